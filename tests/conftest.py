@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: longer-running parity case")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import load_oracle
+    return load_oracle()
+
+
+@pytest.fixture(scope="session")
+def reflib():
+    """oracle/_ref (the reference's host sources compiled where they lie); None if not built."""
+    from oracle import load_ref
+    return load_ref()
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
