@@ -1,0 +1,118 @@
+/* qmha.h — C-ABI of the B200-native quantised multi-head-attention forward.
+ *
+ * This is the drop-in boundary for the reference's hot path.  Every entry point takes plain
+ * pointers and sizes (no torch / C++ types) so it can be bound from ctypes, pybind, cgo, JNI …
+ * Citations are file:line in the reference tree (MattJBorowski1991/QuantizedMHA).
+ *
+ *   solve()                 == include/launchers.h:9-10 (defined once per mha_kernels/<k>.cu,
+ *                              e.g. fa_tc_int8_b.cu:600-609); same symbol, same signature,
+ *                              same "complete on return" behaviour (launchers.h:64).
+ *   qmha_forward()          replaces launchers.h:16-72 launch<KernelFn>() + the per-head
+ *                              extract/kernel/concat loop; adds batch, stream, variant.
+ *   qmha_quantize_*()       expose kernel (a), the replacement of fp32_to_int8sram
+ *                              (fa_tc_int8_b.cu:33-152), for bit-exact checks.
+ *   qmha_attention_prepared() exposes kernel (b)/(c), the replacement of fa_kernel
+ *                              (fa_tc_int8_b.cu:408-579 / fa_tc_v2a.cu:274-496).
+ *
+ * Error model: solve() stays void and never throws (the reference ignores CUDA errors inside
+ * launch(), launchers.h:27-71); every other entry returns 0 on success, non-zero on failure,
+ * and qmha_last_error() returns a message for the calling thread.  There is NO CPU fallback:
+ * without an sm_100 device every compute entry fails with an error.
+ */
+#ifndef QMHA_H
+#define QMHA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Kernel variants (selected per call; solve() uses the build/runtime default, see below). */
+#define QMHA_KERNEL_INT8 0 /* Q·K^T tcgen05 kind::i8, P·V kind::f16; replaces fa_tc_int8_a/b   */
+#define QMHA_KERNEL_F16 1  /* Q·K^T and P·V tcgen05 kind::f16; replaces fa_tc_v1a..v2b, fa, unfused */
+
+/* Granularity of the dynamic INT8 scales (symmetric, zero-point free, fa_tc_int8_b.cu:104). */
+#define QMHA_GRAN_TENSOR 0 /* one scale per tensor                                   */
+#define QMHA_GRAN_HEAD 1   /* one scale per (batch, head) slab [N, d]  (default)     */
+#define QMHA_GRAN_BLOCK 2  /* one scale per (batch, head, 32-row block): reference granularity;
+                              supported by qmha_quantize_blocks only in this round       */
+
+/* ---- the reference's own entry point -------------------------------------------------------
+ * include/launchers.h:9-10.  Q,K,V,output: DEVICE pointers, fp32, contiguous row-major
+ * [N, d_model]; head j occupies columns [j*d, (j+1)*d), d = d_model / h.  Synchronous on return.
+ * Unlike the reference, N, d_model and h are honoured at run time (d <= 128, d % 4 == 0).
+ * The variant is the library default: QMHA_DEFAULT_KERNEL at build time (Makefile KERNEL=),
+ * overridable with qmha_set_kernel() or the QMHA_KERNEL environment variable; the reference's
+ * kernel names are accepted (fa_tc_int8_a/b -> INT8; fa, unfused, fa_tc_v1a..v2b -> F16). */
+void solve(const float* Q, const float* K, const float* V, float* output, int N, int d_model,
+           int h);
+
+/* ---- extended, stream-ordered entry --------------------------------------------------------
+ * Q,K,V,O: DEVICE pointers, fp32, contiguous [B, N, d_model].  `stream` is a cudaStream_t
+ * (NULL = legacy default stream).  Asynchronous: returns after enqueueing.  Scratch (int8 /
+ * fp16 operands, scales) lives in a per-device workspace grown on demand and reused. */
+int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B, int N,
+                 int d_model, int h, int kernel, int gran, void* stream);
+
+/* Same computation from HOST buffers (pageable or pinned): H2D, compute and D2H are pipelined
+ * over batch×head-group chunks on internal streams; synchronous on return.  This is what
+ * bench.py's `e2e` figure times. */
+int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, int B, int N,
+                      int d_model, int h, int kernel, int gran);
+
+/* ---- operand preparation (kernel (a)) ------------------------------------------------------
+ * Internal operand layout ("prepared" tensors), u = b*h + head:
+ *   Qp, Kp : [B*h, n_pad, d_pad]   int8 (INT8 variant) or fp16 (F16 variant), zero padded
+ *   Vt     : [B*h, d_pad, n_pad]   fp16, TRANSPOSED (keys contiguous); for INT8 the values are
+ *                                   the int8 codes stored exactly in fp16
+ *   scales : [3, B*h] fp32 (Q, K, V) — for QMHA_GRAN_TENSOR every entry of a row is equal
+ * n_pad = N rounded up to 256, d_pad = 32/64/128 >= d. */
+int qmha_workspace_dims(int N, int d_model, int h, int* n_pad, int* d_pad);
+
+/* Dynamic absmax quantisation, kernel spec (fa_tc_int8_b.cu:104-106,136-140):
+ * sc = max(absmax/127, 1e-8), q = clamp(rint(v * (1.0f/sc)), -128, 127). */
+int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int N, int d_model,
+                      int h, int gran, int8_t* Qp, int8_t* Kp, uint16_t* Vt, float* scales,
+                      void* stream);
+
+/* fp32 -> fp16 operand conversion for the F16 variant (fa_tc_v1a.cu:267,321,348 convert on
+ * load; here it is one HBM-bound pre-pass).  Qp/Kp are fp16 stored as uint16_t. */
+int qmha_convert_qkv_f16(const float* Q, const float* K, const float* V, int B, int N,
+                         int d_model, int h, uint16_t* Qp, uint16_t* Kp, uint16_t* Vt,
+                         void* stream);
+
+/* Reference-granularity quantisation of ONE tensor in the INPUT layout [B, N, d_model]:
+ * one scale per (batch, head, block of block_rows rows) exactly like fp32_to_int8sram on a
+ * Br x d tile.  q has the input layout; scales is [B*h*ceil(N/block_rows)]. */
+int qmha_quantize_blocks(const float* X, int B, int N, int d_model, int h, int block_rows,
+                         int8_t* q, float* scales, void* stream);
+
+/* Static-scale quantisation, golden spec (tests/generate_golden.cpp:94-101):
+ * q = clamp((int)round(x/scale + zero_point), -128, 127), round half away from zero. */
+int qmha_quantize_static(const float* X, int64_t n, float scale, float zero_point, int8_t* q,
+                         void* stream);
+
+/* ---- attention on prepared operands (kernel (b)/(c)) --------------------------------------- */
+int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt,
+                            const float* scales, float* O, int B, int N, int d_model, int h,
+                            int kernel, void* stream);
+
+/* qmha_forward()/qmha_attention_prepared() are asynchronous; after synchronising the stream,
+ * this reports (and clears) a device-side pipeline failure recorded by the kernel. */
+int qmha_check_async_error(void);
+
+/* ---- housekeeping -------------------------------------------------------------------------- */
+const char* qmha_last_error(void);          /* "" when the last call on this thread succeeded */
+int qmha_set_kernel(const char* name);      /* default variant used by solve(); 0 = ok        */
+const char* qmha_get_kernel(void);          /* "int8" or "f16"                                */
+int qmha_kernel_from_name(const char* name); /* QMHA_KERNEL_* or -1                           */
+int64_t qmha_launch_count(void);            /* kernels launched by this library so far        */
+void qmha_shutdown(void);                   /* frees every per-device workspace               */
+const char* qmha_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMHA_H */

@@ -1,0 +1,245 @@
+"""ctypes binding of quantizedmha_b200/lib/libqmha.so (include/qmha.h).
+
+PyTorch appears here only for device memory, streams and pointers — the reference's own torch
+extension does the same (extensions/torch/torch_ext.cpp:36-40 passes raw data_ptr()s to solve).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+KERNEL_INT8, KERNEL_F16 = 0, 1
+GRAN_TENSOR, GRAN_HEAD, GRAN_BLOCK = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB: Optional[C.CDLL] = None
+
+
+class QmhaError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.environ.get("QMHA_LIB", os.path.join(_HERE, "lib", "libqmha.so"))
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise QmhaError(f"{p} not found: build it with `make lib` or __graft_entry__.build(); "
+                            "there is no fallback path")
+        L = C.CDLL(p)
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.solve.argtypes = [vp, vp, vp, vp, i, i, i]
+        L.solve.restype = None
+        L.qmha_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
+        L.qmha_forward_host.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i]
+        L.qmha_workspace_dims.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+        L.qmha_quantize_qkv.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp]
+        L.qmha_convert_qkv_f16.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
+        L.qmha_quantize_blocks.argtypes = [vp, i, i, i, i, i, vp, vp, vp]
+        L.qmha_quantize_static.argtypes = [vp, C.c_int64, f, f, vp, vp]
+        L.qmha_attention_prepared.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp]
+        L.qmha_check_async_error.argtypes = []
+        L.qmha_last_error.restype = C.c_char_p
+        L.qmha_set_kernel.argtypes = [C.c_char_p]
+        L.qmha_get_kernel.restype = C.c_char_p
+        L.qmha_kernel_from_name.argtypes = [C.c_char_p]
+        L.qmha_launch_count.restype = C.c_int64
+        L.qmha_version.restype = C.c_char_p
+        L.qmha_shutdown.restype = None
+        _LIB = L
+    return _LIB
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise QmhaError(lib().qmha_last_error().decode() or "qmha call failed")
+
+
+def kernel_id(kernel) -> int:
+    """Accepts KERNEL_* ints, 'int8'/'f16', or any of the reference's kernel names."""
+    if isinstance(kernel, int):
+        return kernel
+    k = lib().qmha_kernel_from_name(str(kernel).encode())
+    if k < 0:
+        raise QmhaError(f"unknown kernel {kernel!r}")
+    return k
+
+
+def launch_count() -> int:
+    return int(lib().qmha_launch_count())
+
+
+def workspace_dims(N: int, d_model: int, h: int) -> Tuple[int, int]:
+    n_pad, d_pad = C.c_int(), C.c_int()
+    _check(lib().qmha_workspace_dims(N, d_model, h, C.byref(n_pad), C.byref(d_pad)))
+    return n_pad.value, d_pad.value
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream_ptr(stream=None) -> int:
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+def _shape3(t) -> Tuple[int, int, int]:
+    if t.dim() == 2:
+        return 1, t.shape[0], t.shape[1]
+    if t.dim() == 3:
+        return t.shape[0], t.shape[1], t.shape[2]
+    raise QmhaError("expected [N, d_model] or [B, N, d_model]")
+
+
+def _check_inputs(Q, K, V):
+    torch = _torch()
+    for name, t in (("Q", Q), ("K", K), ("V", V)):
+        if not t.is_cuda:
+            raise QmhaError("Inputs must be CUDA tensors")  # torch_ext.cpp:14
+        if t.dtype != torch.float32:
+            raise QmhaError(f"{name} must be float32")  # torch_ext.cpp:15-17
+    if Q.shape != K.shape or Q.shape != V.shape:
+        raise QmhaError("Q, K, V must have the same shape")
+
+
+def solve(Q, K, V, N: int, d_model: int, h: int, out=None):
+    """The reference's C entry point on torch device tensors (synchronous, default variant)."""
+    torch = _torch()
+    out = torch.empty_like(Q) if out is None else out
+    torch.cuda.current_stream().synchronize()
+    lib().solve(Q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr(), N, d_model, h)
+    err = lib().qmha_last_error().decode()
+    if err:
+        raise QmhaError(err)
+    return out
+
+
+def forward(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=None, stream=None):
+    """Stream-ordered forward on [N, d_model] or [B, N, d_model] fp32 CUDA tensors."""
+    torch = _torch()
+    _check_inputs(Q, K, V)
+    Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+    B, N, d_model = _shape3(Q)
+    out = torch.empty_like(Q) if out is None else out
+    _check(lib().qmha_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr(), B, N, d_model,
+                              num_heads, kernel_id(kernel), gran, _stream_ptr(stream)))
+    return out
+
+
+def flash_solve(Q, K, V, d_model: int, num_heads: int, kernel: str = "fa_tc_int8_b"):
+    """Mirror of torch_ext.flash_solve (extensions/torch/torch_ext.cpp:11-43): fp32 CUDA tensors
+    whose numel is a multiple of d_model; returns a tensor like Q.  Unlike the reference, `kernel`
+    actually selects the variant and the work is enqueued on torch's current stream."""
+    torch = _torch()
+    _check_inputs(Q, K, V)
+    Qc, Kc, Vc = Q.contiguous(), K.contiguous(), V.contiguous()
+    if Qc.numel() % d_model != 0:
+        raise QmhaError("Q.numel() must be divisible by d_model")  # torch_ext.cpp:24
+    if Qc.dim() == 3:
+        B, N = Qc.shape[0], Qc.shape[1]
+    else:
+        B, N = 1, Qc.numel() // d_model
+    out = torch.empty_like(Qc)
+    _check(lib().qmha_forward(Qc.data_ptr(), Kc.data_ptr(), Vc.data_ptr(), out.data_ptr(), B, N, d_model,
+                              num_heads, kernel_id(kernel), GRAN_HEAD, _stream_ptr()))
+    return out
+
+
+def flash_solve_ptr(q_ptr: int, k_ptr: int, v_ptr: int, out_ptr: int, N: int, d_model: int,
+                    num_heads: int, kernel: str = "fa_tc_int8_b") -> None:
+    """Mirror of jax_ext.flash_solve (extensions/jax/jax_ext.cpp:12-28): raw device addresses."""
+    L = lib()
+    _check(L.qmha_forward(q_ptr, k_ptr, v_ptr, out_ptr, 1, N, d_model, num_heads, kernel_id(kernel),
+                          GRAN_HEAD, None))
+    _torch().cuda.synchronize()
+    _check(L.qmha_check_async_error())
+
+
+def forward_host(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=None):
+    """Host (CPU, ideally pinned) fp32 tensors in, host tensor out; copies are pipelined inside."""
+    torch = _torch()
+    B, N, d_model = _shape3(Q)
+    out = torch.empty_like(Q) if out is None else out
+    _check(lib().qmha_forward_host(Q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr(), B, N, d_model,
+                                   num_heads, kernel_id(kernel), gran))
+    return out
+
+
+def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None):
+    """Kernel (a).  Returns (Qp int8 [B*h,n_pad,d_pad], Kp, Vt fp16 [B*h,d_pad,n_pad], scales [3,B*h])."""
+    torch = _torch()
+    _check_inputs(Q, K, V)
+    Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+    B, N, d_model = _shape3(Q)
+    n_pad, d_pad = workspace_dims(N, d_model, num_heads)
+    u = B * num_heads
+    Qp = torch.empty((u, n_pad, d_pad), dtype=torch.int8, device=Q.device)
+    Kp = torch.empty_like(Qp)
+    Vt = torch.empty((u, d_pad, n_pad), dtype=torch.float16, device=Q.device)
+    scales = torch.empty((3, u), dtype=torch.float32, device=Q.device)
+    _check(lib().qmha_quantize_qkv(Q.data_ptr(), K.data_ptr(), V.data_ptr(), B, N, d_model, num_heads, gran,
+                                   Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), scales.data_ptr(),
+                                   _stream_ptr(stream)))
+    return Qp, Kp, Vt, scales
+
+
+def convert_qkv_f16(Q, K, V, num_heads: int, stream=None):
+    torch = _torch()
+    _check_inputs(Q, K, V)
+    Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+    B, N, d_model = _shape3(Q)
+    n_pad, d_pad = workspace_dims(N, d_model, num_heads)
+    u = B * num_heads
+    Qp = torch.empty((u, n_pad, d_pad), dtype=torch.float16, device=Q.device)
+    Kp = torch.empty_like(Qp)
+    Vt = torch.empty((u, d_pad, n_pad), dtype=torch.float16, device=Q.device)
+    _check(lib().qmha_convert_qkv_f16(Q.data_ptr(), K.data_ptr(), V.data_ptr(), B, N, d_model, num_heads,
+                                      Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), _stream_ptr(stream)))
+    return Qp, Kp, Vt
+
+
+def attention_prepared(Qp, Kp, Vt, scales, B: int, N: int, d_model: int, num_heads: int, kernel="int8",
+                       out=None, stream=None):
+    """Kernel (b)/(c) on prepared operands; returns O [B, N, d_model] fp32."""
+    torch = _torch()
+    out = torch.empty((B, N, d_model), dtype=torch.float32, device=Qp.device) if out is None else out
+    _check(lib().qmha_attention_prepared(Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(),
+                                         scales.data_ptr() if scales is not None else None, out.data_ptr(),
+                                         B, N, d_model, num_heads, kernel_id(kernel), _stream_ptr(stream)))
+    return out
+
+
+def check_async_error() -> None:
+    _check(lib().qmha_check_async_error())
+
+
+def quantize_blocks(X, num_heads: int, block_rows: int = 32, stream=None):
+    """Reference-granularity quantiser (one scale per 32-row block per head), input layout."""
+    torch = _torch()
+    X = X.contiguous()
+    B, N, d_model = _shape3(X)
+    nblk = -(-N // block_rows)
+    q = torch.empty(X.shape, dtype=torch.int8, device=X.device)
+    s = torch.empty((B * num_heads * nblk,), dtype=torch.float32, device=X.device)
+    _check(lib().qmha_quantize_blocks(X.data_ptr(), B, N, d_model, num_heads, block_rows, q.data_ptr(),
+                                      s.data_ptr(), _stream_ptr(stream)))
+    return q, s
+
+
+def quantize_static(X, scale: float, zero_point: float = 0.0, stream=None):
+    """Golden-spec quantiser (generate_golden.cpp:94-101)."""
+    torch = _torch()
+    X = X.contiguous()
+    q = torch.empty(X.shape, dtype=torch.int8, device=X.device)
+    _check(lib().qmha_quantize_static(X.data_ptr(), X.numel(), scale, zero_point, q.data_ptr(),
+                                      _stream_ptr(stream)))
+    return q

@@ -1,0 +1,36 @@
+// attn_fwd.cuh — host-visible interface of the tcgen05 attention kernel (attn_fwd.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace qmha {
+
+struct AttnParams {
+  float* O;             // [B, N, H*d] fp32
+  const float* scales;  // [3, units] (INT8 variant) or nullptr
+  int* error_flag;      // device int: 0 = ok, otherwise the wait site that timed out
+  int B, N, H, d;
+  int n_pad;            // padded sequence length of the prepared operands (multiple of 256)
+  int units;            // B*H
+  int n_kv_tiles;       // ceil(N / 128)
+  float scale_log2;     // log2(e) / sqrt(d)
+};
+
+struct AttnLaunch {
+  const void* Qp;       // [units, n_pad, d_pad] int8 or fp16
+  const void* Kp;       // [units, n_pad, d_pad]
+  const void* Vt;       // [units, d_pad, n_pad] fp16
+  const float* scales;
+  float* O;
+  int* error_flag;
+  int B, N, H, d, n_pad, d_pad;
+  bool int8;
+  cudaStream_t stream;
+  bool units_y_limit_exceeded() const { return (long long)B * H > 65535; }
+};
+
+// Enqueues the kernel; returns false and fills *err on a host-side failure.
+bool launch_attention(const AttnLaunch& a, std::string* err);
+
+}  // namespace qmha

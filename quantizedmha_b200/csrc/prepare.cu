@@ -1,0 +1,298 @@
+// prepare.cu — HBM-bound operand preparation (kernel (a) of the north star).
+//
+// Replaces fp32_to_int8sram (mha_kernels/fa_tc_int8_b.cu:33-152), which the reference runs four
+// times per KV step inside the attention loop (Q re-quantised every step, K/V re-quantised by
+// every query block), and extract_mat/concat_mat (utils/utils.cu:6-22).  Here every element of
+// Q, K, V is read from HBM, quantised ONCE and written in the layout the tcgen05 kernel's TMA
+// descriptors want:
+//      Qp, Kp : [B*h, n_pad, d_pad]  int8 (or fp16 for the FP16 variant)
+//      Vt     : [B*h, d_pad, n_pad]  fp16, transposed so P·V's B operand is K-major
+// Arithmetic is the reference's, bit for bit (fa_tc_int8_b.cu:104-106,136-140):
+//      sc = fmaxf(absmax / 127.0f, 1e-8f);  inv = 1.0f / sc;
+//      q  = clamp(__float2int_rn(v * inv), -128, 127)
+// with one scale per tensor / per (batch, head) / per 32-row block.
+//
+// Kernels:  absmax_kernel  -> per-(batch,head) |x| maxima (128-bit loads, shuffle + smem reduce)
+//           finalize_scales_kernel -> scales from maxima (optionally reduced to per-tensor)
+//           prepare_kernel -> quantise/convert + re-layout (+ transpose of V through smem)
+//           quantize_blocks_kernel / quantize_static_kernel -> reference-granularity and
+//           golden-spec (generate_golden.cpp:94-101) quantisers in the input layout.
+#include <cuda_fp16.h>
+
+#include "prepare.cuh"
+
+namespace qmha {
+
+namespace {
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+__device__ __forceinline__ float absmax4(float m, float4 v) {
+  return fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+}
+
+// fa_tc_int8_b.cu:136-140
+__device__ __forceinline__ int quant1(float v, float inv_sc) {
+  int r = __float2int_rn(v * inv_sc);
+  return r < -128 ? -128 : (r > 127 ? 127 : r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// absmax over [rows r0..r1) of batch b for every head; grid = (row_chunks, B, 3 tensors).
+// amax_bits[z][b*H + head] accumulates max |x| as the bit pattern of a non-negative float
+// (monotone under unsigned compare, so atomicMax works).
+constexpr int kAbsmaxThreads = 256;
+constexpr int kAbsmaxRows = 32;
+
+__global__ void __launch_bounds__(kAbsmaxThreads)
+absmax_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+              const float* __restrict__ V, unsigned* __restrict__ amax_bits, int N, int H, int d) {
+  extern __shared__ unsigned s_amax[];  // [H]
+  const int z = blockIdx.z, b = blockIdx.y;
+  const float* X = z == 0 ? Q : (z == 1 ? K : V);
+  const int d_model = H * d;
+  const int r0 = blockIdx.x * kAbsmaxRows;
+  const int r1 = min(N, r0 + kAbsmaxRows);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) s_amax[i] = 0u;
+  __syncthreads();
+  const float* base = X + ((size_t)b * N) * d_model;
+  if ((d & 3) == 0) {
+    const int vecs = d_model >> 2;
+    for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+      const int head = (v << 2) / d;
+      const float* col = base + (size_t)(v << 2);
+      float m = 0.f;
+      int r = r0;
+      for (; r + 8 <= r1; r += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = ldg_f4(col + (size_t)(r + u) * d_model);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m = absmax4(m, x[u]);
+      }
+      for (; r < r1; ++r) m = absmax4(m, ldg_f4(col + (size_t)r * d_model));
+      atomicMax(&s_amax[head], __float_as_uint(m));
+    }
+  } else {
+    for (int c = threadIdx.x; c < d_model; c += blockDim.x) {
+      float m = 0.f;
+      for (int r = r0; r < r1; ++r) m = fmaxf(m, fabsf(__ldg(base + (size_t)r * d_model + c)));
+      atomicMax(&s_amax[c / d], __float_as_uint(m));
+    }
+  }
+  __syncthreads();
+  unsigned* out = amax_bits + ((size_t)z * gridDim.y + b) * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    if (s_amax[i]) atomicMax(&out[i], s_amax[i]);
+}
+
+// scales[z][u] = fmaxf(amax/127, 1e-8)  (fa_tc_int8_b.cu:104); per-tensor = max over all u first.
+__global__ void finalize_scales_kernel(const unsigned* __restrict__ amax_bits,
+                                       float* __restrict__ scales, int units, int per_tensor) {
+  const int z = blockIdx.x;
+  __shared__ unsigned s_max;
+  if (threadIdx.x == 0) s_max = 0u;
+  __syncthreads();
+  if (per_tensor) {
+    unsigned m = 0u;
+    for (int u = threadIdx.x; u < units; u += blockDim.x) m = max(m, amax_bits[(size_t)z * units + u]);
+    atomicMax(&s_max, m);
+    __syncthreads();
+  }
+  for (int u = threadIdx.x; u < units; u += blockDim.x) {
+    const float a = __uint_as_float(per_tensor ? s_max : amax_bits[(size_t)z * units + u]);
+    scales[(size_t)z * units + u] = fmaxf(a / 127.0f, 1e-8f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepare_kernel: one CTA = one 128-row tile of one (batch, head) of one tensor.
+//   grid = (n_pad/128, B*H, 3);  z = 0:Q 1:K 2:V
+constexpr int kPrepThreads = 256;
+constexpr int kPrepRows = 128;
+
+template <bool kInt8, int kD>
+__global__ void __launch_bounds__(kPrepThreads)
+prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+               const float* __restrict__ V, const float* __restrict__ scales, void* __restrict__ Qp,
+               void* __restrict__ Kp, __half* __restrict__ Vt, int N, int H, int d, int n_pad) {
+  const int z = blockIdx.z, unit = blockIdx.y;
+  const int b = unit / H, head = unit % H;
+  const int n0 = blockIdx.x * kPrepRows;
+  const float* X = z == 0 ? Q : (z == 1 ? K : V);
+  const int d_model = H * d;
+  const float* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+  float inv_sc = 1.0f;
+  if constexpr (kInt8) inv_sc = 1.0f / scales[(size_t)z * gridDim.y + unit];  // fa_tc_int8_b.cu:106
+
+  constexpr int kVecPerRow = kD / 4;                   // float4 slots per padded row
+  constexpr int kRowsPerIter = kPrepThreads / kVecPerRow;
+  const int vec = threadIdx.x % kVecPerRow;
+  const int rsub = threadIdx.x / kVecPerRow;
+  const bool vec_ok = (d & 3) == 0;
+
+  auto load4 = [&](int n, int c, float (&x)[4]) {
+    x[0] = x[1] = x[2] = x[3] = 0.f;
+    if (n < N) {
+      const float* p = src + (size_t)n * d_model + c;
+      if (vec_ok) {
+        if (c < d) { float4 v = ldg_f4(p); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (c + e < d) x[e] = __ldg(p + e);
+      }
+    }
+  };
+
+  if (z < 2) {
+    void* dst = z == 0 ? Qp : Kp;
+#pragma unroll 4
+    for (int r = rsub; r < kPrepRows; r += kRowsPerIter) {
+      const int n = n0 + r;
+      float x[4];
+      load4(n, vec * 4, x);
+      const size_t o = ((size_t)unit * n_pad + n) * kD + vec * 4;
+      if constexpr (kInt8) {
+        const int q0 = quant1(x[0], inv_sc), q1 = quant1(x[1], inv_sc);
+        const int q2 = quant1(x[2], inv_sc), q3 = quant1(x[3], inv_sc);
+        const uint32_t pk = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) |
+                            ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(dst) + o) = pk;
+      } else {
+        __half2 h01 = __floats2half2_rn(x[0], x[1]);
+        __half2 h23 = __floats2half2_rn(x[2], x[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h01);
+        pk.y = *reinterpret_cast<uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dst) + o) = pk;
+      }
+    }
+  } else {
+    // V: quantise/convert into a shared tile, then write it transposed (keys contiguous).
+    constexpr int kStride = kD + 2;  // halves; odd word stride spreads the transposed reads
+    __shared__ __half tile[kPrepRows * kStride];
+    for (int r = rsub; r < kPrepRows; r += kRowsPerIter) {
+      float x[4];
+      load4(n0 + r, vec * 4, x);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float y = x[e];
+        if constexpr (kInt8) y = (float)quant1(x[e], inv_sc);  // int8 code, exact in fp16
+        tile[r * kStride + vec * 4 + e] = __float2half_rn(y);
+      }
+    }
+    __syncthreads();
+    // each thread emits 2 consecutive keys (4 bytes) of one d-row; 64 threads cover 128 keys.
+    const int kp = threadIdx.x & 63;
+    for (int dd = threadIdx.x >> 6; dd < kD; dd += kPrepThreads / 64) {
+      __half2 o2 = __halves2half2(tile[(2 * kp) * kStride + dd], tile[(2 * kp + 1) * kStride + dd]);
+      *reinterpret_cast<__half2*>(Vt + ((size_t)unit * kD + dd) * n_pad + n0 + 2 * kp) = o2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference-granularity quantiser in the input layout: one warp per (batch, head, row block).
+__global__ void quantize_blocks_kernel(const float* __restrict__ X, int8_t* __restrict__ q,
+                                       float* __restrict__ scales, int B, int N, int H, int d,
+                                       int block_rows, int nblk) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const long long blk_id = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  const long long total = (long long)B * H * nblk;
+  if (blk_id >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int blk = (int)(blk_id % nblk);
+  const int head = (int)((blk_id / nblk) % H);
+  const int b = (int)(blk_id / ((long long)nblk * H));
+  const int d_model = H * d;
+  const int r0 = blk * block_rows, rows = min(block_rows, N - r0);
+  const size_t base = ((size_t)b * N + r0) * d_model + (size_t)head * d;
+  const int elems = rows * d;
+  float m = 0.f;
+  for (int i = lane; i < elems; i += 32)
+    m = fmaxf(m, fabsf(X[base + (size_t)(i / d) * d_model + (i % d)]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  const float sc = fmaxf(m / 127.0f, 1e-8f);
+  const float inv = 1.0f / sc;
+  if (lane == 0) scales[blk_id] = sc;
+  for (int i = lane; i < elems; i += 32) {
+    const size_t o = base + (size_t)(i / d) * d_model + (i % d);
+    q[o] = (int8_t)quant1(X[o], inv);
+  }
+}
+
+// Golden spec (generate_golden.cpp:94-101): round half away from zero, true division.
+__global__ void quantize_static_kernel(const float* __restrict__ X, int8_t* __restrict__ q,
+                                       long long n, float scale, float zp) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int v = (int)roundf(X[i] / scale + zp);
+    v = v > 127 ? 127 : (v < -128 ? -128 : v);
+    q[i] = (int8_t)v;
+  }
+}
+
+template <bool kInt8, int kD>
+cudaError_t launch_prepare_cfg(const PrepareArgs& a) {
+  dim3 grid(a.n_pad / kPrepRows, a.B * a.H, 3);
+  prepare_kernel<kInt8, kD><<<grid, kPrepThreads, 0, a.stream>>>(
+      a.Q, a.K, a.V, a.scales, a.Qp, a.Kp, reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_absmax_and_scales(const PrepareArgs& a, unsigned* amax_bits, int per_tensor) {
+  const int units = a.B * a.H;
+  cudaError_t e = cudaMemsetAsync(amax_bits, 0, sizeof(unsigned) * 3 * units, a.stream);
+  if (e != cudaSuccess) return e;
+  dim3 grid((a.N + kAbsmaxRows - 1) / kAbsmaxRows, a.B, 3);
+  absmax_kernel<<<grid, kAbsmaxThreads, sizeof(unsigned) * a.H, a.stream>>>(a.Q, a.K, a.V, amax_bits,
+                                                                           a.N, a.H, a.d);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  finalize_scales_kernel<<<3, 256, 0, a.stream>>>(amax_bits, a.scales, units, per_tensor);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prepare(const PrepareArgs& a) {
+  if (a.int8) {
+    switch (a.d_pad) {
+      case 32: return launch_prepare_cfg<true, 32>(a);
+      case 64: return launch_prepare_cfg<true, 64>(a);
+      case 128: return launch_prepare_cfg<true, 128>(a);
+    }
+  } else {
+    switch (a.d_pad) {
+      case 32: return launch_prepare_cfg<false, 32>(a);
+      case 64: return launch_prepare_cfg<false, 64>(a);
+      case 128: return launch_prepare_cfg<false, 128>(a);
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_quantize_blocks(const float* X, int B, int N, int H, int d, int block_rows,
+                                   int8_t* q, float* scales, cudaStream_t stream) {
+  const int nblk = (N + block_rows - 1) / block_rows;
+  const long long total = (long long)B * H * nblk;
+  const int warps = 8;
+  const unsigned grid = (unsigned)((total + warps - 1) / warps);
+  quantize_blocks_kernel<<<grid, warps * 32, 0, stream>>>(X, q, scales, B, N, H, d, block_rows, nblk);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quantize_static(const float* X, long long n, float scale, float zp, int8_t* q,
+                                   cudaStream_t stream) {
+  const int threads = 256;
+  long long blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  quantize_static_kernel<<<(unsigned)blocks, threads, 0, stream>>>(X, q, n, scale, zp);
+  return cudaGetLastError();
+}
+
+}  // namespace qmha

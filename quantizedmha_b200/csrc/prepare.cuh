@@ -1,0 +1,30 @@
+// prepare.cuh — host-visible interface of the operand-preparation kernels (prepare.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qmha {
+
+struct PrepareArgs {
+  const float* Q;  // [B, N, H*d] fp32, device
+  const float* K;
+  const float* V;
+  float* scales;   // [3, B*H] (INT8) — written by launch_absmax_and_scales, read by launch_prepare
+  void* Qp;        // [B*H, n_pad, d_pad] int8 / fp16
+  void* Kp;
+  void* Vt;        // [B*H, d_pad, n_pad] fp16
+  int B, N, H, d, n_pad, d_pad;
+  bool int8;
+  cudaStream_t stream;
+};
+
+// absmax pass + scale finalisation (3 launches incl. the memset node).
+cudaError_t launch_absmax_and_scales(const PrepareArgs& a, unsigned* amax_bits, int per_tensor);
+// quantise / convert + re-layout (1 launch).
+cudaError_t launch_prepare(const PrepareArgs& a);
+cudaError_t launch_quantize_blocks(const float* X, int B, int N, int H, int d, int block_rows,
+                                   int8_t* q, float* scales, cudaStream_t stream);
+cudaError_t launch_quantize_static(const float* X, long long n, float scale, float zp, int8_t* q,
+                                   cudaStream_t stream);
+
+}  // namespace qmha
