@@ -32,18 +32,14 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
 
-# api.o carries the default variant, so it is rebuilt per KERNEL.
-$(OBJDIR)/api_$(KERNEL).o: $(CSRC)/api.cu $(HDRS)
+# api_<KERNEL>.o carries the default variant of solve(), so there is one per KERNEL.
+$(OBJDIR)/api_%.o: $(CSRC)/api.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVCCFLAGS) -DQMHA_DEFAULT_KERNEL='"$(KERNEL)"' -c $< -o $@
+	$(NVCC) $(NVCCFLAGS) -DQMHA_DEFAULT_KERNEL='"$*"' -c $< -o $@
 
 $(LIB): $(KOBJS) $(OBJDIR)/api_fa_tc_int8_b.o
 	@mkdir -p $(LIBDIR)
 	$(NVCC) -shared $(GENCODE) -o $@ $^
-
-$(OBJDIR)/api_fa_tc_int8_b.o: $(CSRC)/api.cu $(HDRS)
-	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVCCFLAGS) -DQMHA_DEFAULT_KERNEL='"fa_tc_int8_b"' -c $< -o $@
 
 driver: bin/profile_$(KERNEL)
 

@@ -1,0 +1,146 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol declared
+in include/qmha.h, argument validation / error reporting, the loud no-GPU failure, and the
+(batch × head) sharding used for multi-GPU runs (world_size 2 over gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def qm():
+    import quantizedmha_b200 as q
+    if not os.path.exists(q.lib_path()):
+        import __graft_entry__ as g
+        g.build()
+    return q
+
+
+def test_library_exports_every_declared_symbol(qm):
+    hdr = open(os.path.join(ROOT, "include", "qmha.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(solve|qmha_[a-z0-9_]+)\s*\(", hdr))
+    assert {"solve", "qmha_forward", "qmha_forward_host", "qmha_quantize_qkv", "qmha_attention_prepared",
+            "qmha_quantize_blocks", "qmha_quantize_static", "qmha_convert_qkv_f16", "qmha_last_error"} <= names
+    L = ctypes.CDLL(qm.lib_path())
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in include/qmha.h but not exported"
+
+
+def test_launchers_header_is_the_reference_signature():
+    txt = open(os.path.join(ROOT, "include", "qmha.h")).read()
+    flat = " ".join(txt.split())
+    assert "void solve(const float* Q, const float* K, const float* V, float* output, int N, int d_model, int h);" in flat
+
+
+def test_kernel_name_aliases(qm):
+    for n in ("fa_tc_int8_b", "fa_tc_int8_a", "int8", "fa_b200_int8"):
+        assert qm.kernel_id(n) == qm.KERNEL_INT8
+    for n in ("fa_tc_v2a", "fa_tc_v1a", "fa", "unfused", "f16", "fa_b200_f16"):
+        assert qm.kernel_id(n) == qm.KERNEL_F16
+    with pytest.raises(qm.QmhaError):
+        qm.kernel_id("no_such_kernel")
+
+
+def test_workspace_dims_and_shape_validation(qm):
+    assert qm.workspace_dims(8192, 4096, 32) == (8192, 128)
+    assert qm.workspace_dims(50, 64, 8) == (256, 32)
+    assert qm.workspace_dims(4096, 512, 8) == (4096, 64)
+    with pytest.raises(qm.QmhaError, match="divisible"):
+        qm.workspace_dims(128, 100, 3)
+    with pytest.raises(qm.QmhaError, match="<= 128"):
+        qm.workspace_dims(128, 512, 2)
+
+
+def test_no_gpu_means_loud_failure_not_fallback(qm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rc = qm.lib().qmha_forward(None, None, None, None, 1, 8, 32, 4, 0, 1, None)
+    assert rc != 0 and b"no CPU fallback" in qm.lib().qmha_last_error()
+    rc = qm.lib().qmha_forward_host(None, None, None, None, 1, 8, 32, 4, 0, 1)
+    assert rc != 0
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "quantizedmha_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower().replace("# oracle", ""), f"{f} references the oracle"
+
+
+def test_unit_sharding_partitions_exactly():
+    from quantizedmha_b200.sharding import shard_slabs, unit_range
+    for B, H, W in [(8, 32, 8), (8, 32, 3), (1, 8, 2), (5, 7, 4), (2, 3, 8)]:
+        seen = []
+        for r in range(W):
+            lo, hi = unit_range(B * H, W, r)
+            got = [b * H + h for (b, h0, h1) in shard_slabs(B, H, W, r) for h in range(h0, h1)]
+            assert got == list(range(lo, hi))
+            seen += got
+        assert seen == list(range(B * H))
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from oracle import load_oracle
+from quantizedmha_b200.sharding import shard_slabs, slab_view
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+orc = load_oracle()
+B, N, H, d = 2, 48, 3, 8
+q, k, v = orc.profile_inputs(B * N, H * d)
+q, k, v = (a.reshape(B, N, H * d) for a in (q, k, v))
+full = orc.mha(q, k, v, H, threads=1)
+mine = np.zeros_like(full)
+for (b, h0, h1) in shard_slabs(B, H, world, rank):
+    o = orc.mha(np.ascontiguousarray(slab_view(q, b, h0, h1, H)), np.ascontiguousarray(slab_view(k, b, h0, h1, H)),
+                np.ascontiguousarray(slab_view(v, b, h0, h1, H)), h1 - h0, threads=1)
+    mine[b, :, h0 * d:h1 * d] = o
+t = torch.from_numpy(mine)
+dist.all_reduce(t)  # disjoint shards: the sum is the concatenation (test-side gather only)
+times = torch.tensor([float(rank + 1)])
+dist.all_reduce(times, op=dist.ReduceOp.MAX)
+assert times.item() == float(world)
+assert np.array_equal(t.numpy(), full), "sharded result differs from the unsharded oracle"
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    """The multi-GPU path is 'each rank runs its own units, no collective on the data path'.
+    Two CPU ranks each compute their shard with the oracle; the union must equal the whole."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    port = 29500 + (os.getpid() % 400)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out.decode()
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """bench.py --impl reference runs the reference's CPU path on the host cores only."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample-n", "256", "--cpu-sample-heads", "2"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "TFLOP/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
