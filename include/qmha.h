@@ -103,6 +103,13 @@ int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt,
  * this reports (and clears) a device-side pipeline failure recorded by the kernel. */
 int qmha_check_async_error(void);
 
+/* Debug/tuning aid: runs the instrumented INT8 d=128 attention kernel once (synchronous) and
+ * returns the clock64 timeline of CTA (0,0): host_trace[3][ceil(N/64)][4] (softmax tile 0,
+ * softmax tile 1, MMA issuer).  variant k: polynomial exp2 on every k-th pair (0 = none). */
+int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* Vt,
+                               const float* scales, float* O, int B, int N, int d_model, int h,
+                               int variant, long long* host_trace);
+
 /* ---- housekeeping -------------------------------------------------------------------------- */
 const char* qmha_last_error(void);          /* "" when the last call on this thread succeeded */
 int qmha_set_kernel(const char* name);      /* default variant used by solve(); 0 = ok        */

@@ -17,6 +17,9 @@
 #ifndef QMHA_DEFAULT_KERNEL
 #define QMHA_DEFAULT_KERNEL "fa_tc_int8_b"
 #endif
+#ifndef QMHA_DEFAULT_ATTN_VARIANT
+#define QMHA_DEFAULT_ATTN_VARIANT 0
+#endif
 
 namespace {
 
@@ -162,9 +165,18 @@ int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, i
   return 0;
 }
 
+// Kernel variant k: exp2 of every k-th score pair on the FMA-pipe polynomial (0 = all MUFU).
+// QMHA_ATTN_VARIANT overrides the built-in default (tuning / A-B measurements).
+int attention_variant(int kernel) {
+  const char* env = getenv("QMHA_ATTN_VARIANT");
+  if (env && *env) return atoi(env);
+  (void)kernel;
+  return QMHA_DEFAULT_ATTN_VARIANT;
+}
+
 int attention_impl(const void* Qp, const void* Kp, const void* Vt, const float* scales, float* O,
                    int B, int N, int d_model, int h, int kernel, int* error_flag,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, long long* trace = nullptr, int variant = -1) {
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   if (check_aligned16(O, "output")) return 1;
@@ -173,6 +185,8 @@ int attention_impl(const void* Qp, const void* Kp, const void* Vt, const float* 
   a.B = B; a.N = N; a.H = h; a.d = d; a.n_pad = n_pad; a.d_pad = d_pad;
   a.int8 = kernel == QMHA_KERNEL_INT8;
   a.stream = stream;
+  a.trace = trace;
+  a.variant = variant >= 0 ? variant : attention_variant(kernel);
   std::string err;
   if (!qmha::launch_attention(a, &err)) return fail(err);
   g_launches += 1;
@@ -303,6 +317,32 @@ int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B
     return 1;
   g_err.clear();
   return 0;
+}
+
+// Debug: runs the traced INT8 d=128 kernel once (synchronously) and copies the timeline of CTA
+// (0,0) to host_trace[3][ceil(N/64)][4] (clock64 stamps: softmax tile 0, softmax tile 1, MMA).
+int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* Vt,
+                               const float* scales, float* O, int B, int N, int d_model, int h,
+                               int variant, long long* host_trace) {
+  const int dev = require_device();
+  if (dev < 0) return 1;
+  Workspace* w;
+  if (get_workspace(dev, 0, 0, 0, &w)) return 1;
+  const size_t n = (size_t)3 * ((N + 63) / 64) * 4;
+  long long* dtrace = nullptr;
+  cudaError_t e = cudaMalloc(&dtrace, n * sizeof(long long));
+  if (e != cudaSuccess) return fail_cuda("cudaMalloc(trace)", e);
+  cudaMemset(dtrace, 0, n * sizeof(long long));
+  int rc = attention_impl(Qp, Kp, Vt, scales, O, B, N, d_model, h, QMHA_KERNEL_INT8, w->error_flag,
+                          nullptr, dtrace, variant);
+  if (rc == 0) {
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = fail_cuda("trace run", e);
+    else cudaMemcpy(host_trace, dtrace, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dtrace);
+  if (rc == 0) g_err.clear();
+  return rc;
 }
 
 // Checks the asynchronous failure flag of the current device after the caller synchronised.

@@ -5,19 +5,25 @@
 // (softmax(Q·K^T/sqrt(d))·V per head, FP32 statistics and output) — different machine:
 //
 //   * one CTA owns TWO 128-row query tiles of one (batch, head) unit and walks the KV sequence
-//     in 128-key tiles;
+//     in 128-key tiles that are processed as two pipelined 64-key HALF-STEPS;
 //   * warps 8-11 form a service warpgroup (register budget handed to the softmax warps with
-//     setmaxnreg); warp 9 is the TMA producer: Q once, then K and V^T tiles through two mbarrier rings;
-//   * warp 8 (one elected lane) issues every tcgen05.mma:  S_t = Q_t·K_j^T  (kind::i8, int32
-//     accumulators in TMEM — or kind::f16 for the FP16 variant) and  O_t += P_t·V_j
-//     (kind::f16, A operand = P read straight from TMEM, B = V^T tile in shared memory);
+//     setmaxnreg); warp 9 is the TMA producer: Q once, then K and V^T tiles through two
+//     mbarrier rings;
+//   * warp 8 (one elected lane) issues every tcgen05.mma:  S_t[b] = Q_t·K_half^T  (kind::i8,
+//     int32 accumulators in TMEM — kind::f16 for the FP16 variant) into a DOUBLE-BUFFERED score
+//     tile, and  O_t += P_t[b]·V_half  (kind::f16, A operand = P read straight from TMEM,
+//     B = V^T tile in shared memory).  S_t for half-step i+2 is issued right behind P·V of
+//     half-step i, so the softmax warps always find their next scores waiting: the tensor-core
+//     round trip is off the softmax critical path;
 //   * warps 0-3 / 4-7 are the softmax warpgroups of tile 0 / tile 1: one thread per query row,
-//     S read with tcgen05.ld, dequant scale folded into the exponent FMA, exp2 on packed fp16
-//     (INT8 variant) or fp32 (FP16 variant), P written back over S with tcgen05.st, running
-//     row sum in FP32, lazy rescale of O in TMEM only when the row max grows by more than 2^4;
+//     S read with tcgen05.ld, dequant scale folded into the exponent FMA (packed FFMA2), exp2
+//     on the MUFU with an optional share on the FMA pipe (Cody-Waite + cubic polynomial), P
+//     written back over S with tcgen05.st, running row sum in FP32, lazy rescale of O in TMEM
+//     only when the row max grows by more than 2^4;
 //   * epilogue: O·(sV/l) from TMEM to global memory in the reference's [N, h·d] layout.
 //
-// TMEM plan (512 columns): S0|P0 = [0,128)  S1|P1 = [128,256)  O0 = [256,384)  O1 = [384,512).
+// TMEM plan (512 columns): S0[0]|P0[0] = [0,64)  S0[1]|P0[1] = [64,128)  S1[0] = [128,192)
+//                          S1[1] = [192,256)  O0 = [256,384)  O1 = [384,512).
 #include "attn_fwd.cuh"
 #include "sm100_ptx.cuh"
 
@@ -28,14 +34,15 @@ using namespace ptx;
 namespace {
 
 constexpr int kBM = 128;        // query rows per tile == UMMA M
-constexpr int kBN = 128;        // keys per KV tile   == UMMA N of Q·K^T
+constexpr int kBN = 128;        // keys per KV tile in shared memory (one TMA stage)
+constexpr int kHN = 64;         // keys per half-step == UMMA N of Q·K^T, UMMA K extent of P·V
 constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr int kThreads = 384;            // 2 softmax warpgroups + 1 service warpgroup (MMA, TMA, 2 idle)
 constexpr int kRegsSoftmax = 208;        // setmaxnreg budgets: 2*128*208 + 128*72 = 62464 <= 65536
 constexpr int kRegsService = 72;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
+constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;  // S_t[b] at kColS_t + 64*b
 constexpr float kRescaleThreshold = 4.0f;  // log2 units: P <= 2^4, well inside fp16
 constexpr int kMagicI2F = 0x4B400000;      // float(1.5 * 2^23): int -> float by bit tricks
 constexpr float kMagicF = 12582912.0f;
@@ -51,7 +58,8 @@ struct Cfg {
   static constexpr int kStepsQK = kRowBytesQK / 32;                     // UMMA K steps (32 B each)
   static constexpr int kTileBytesV = kD * kBN * 2;                      // V^T tile: kD x 128 fp16
   static constexpr int kSubBytesV = kD * 128;                           // 64 keys x kD rows
-  static constexpr int kStepsPV = kBN / 16;
+  static constexpr int kStepsPV = kHN / 16;                             // UMMA K steps per half-step
+  static constexpr int kHalfBytesQK = kHN * kAtomQK;                    // byte offset of K rows 64.. in a sub-tile
   static constexpr int kBudget = 200 * 1024 - 2 * kTileBytesQK;
   static constexpr int kStagesRaw = kBudget / (kTileBytesQK + kTileBytesV);
   static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;       // K and V ring depth
@@ -59,8 +67,8 @@ struct Cfg {
   static constexpr int kSmemTiles = 2 * kTileBytesQK + kStages * (kTileBytesQK + kTileBytesV);
   static constexpr int kSmemBytes = kSmemTiles + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr uint32_t kIdescQK =
-      kInt8 ? make_idesc(kAccS32, kFmtS8, kFmtS8, kBM, kBN)
-            : make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kBN);
+      kInt8 ? make_idesc(kAccS32, kFmtS8, kFmtS8, kBM, kHN)
+            : make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kHN);
   static constexpr uint32_t kIdescPV = make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kD);
 };
 
@@ -68,7 +76,8 @@ struct Barriers {
   uint64_t q_full;
   uint64_t k_full[4], k_empty[4];
   uint64_t v_full[4], v_empty[4];
-  uint64_t s_full[2], p_full[2], pv_done[2];
+  uint64_t s_full[2][2], p_full[2][2], pv_done[2];  // [tile][buffer]
+  uint64_t o_final[2];                              // one-shot: last P·V of the tile retired
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -96,23 +105,23 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
 }
 
 // ------------------------------------------------------------------------------------------------
-// One softmax step for one thread (= one query row) over a 128-key tile.
-//   s[128]  : raw S row from TMEM (int32 for INT8, fp32 bits for FP16)
+// One softmax step for one thread (= one query row) over a 64-key half-step.
+//   s[64]   : raw S row of the half-step from TMEM (int32 for INT8, fp32 bits for FP16)
 //   c       : logits-to-log2 factor (sQ*sK*log2e/sqrt(d) or log2e/sqrt(d))
 //   m_used  : the (lazily updated) reference max in log2 units
-// Produces p[64] (packed fp16x2 P row) and adds the row sum into l0/l1.
+// Produces p[32] (packed fp16x2 P row) and adds the row sum into the lsum accumulators.
 template <bool kInt8, bool kMasked>
-__device__ __forceinline__ float tile_row_max(uint32_t (&s)[128], float c, int n_valid) {
+__device__ __forceinline__ float tile_row_max(uint32_t (&s)[kHN], float c, int n_valid) {
   if constexpr (kInt8) {
     if constexpr (kMasked) {
 #pragma unroll
-      for (int i = 0; i < 128; ++i)
+      for (int i = 0; i < kHN; ++i)
         if (i >= n_valid) s[i] = (uint32_t)(-(1 << 22));
     }
     int m0 = max((int)s[0], (int)s[1]), m1 = max((int)s[2], (int)s[3]);
     int m2 = max((int)s[4], (int)s[5]), m3 = max((int)s[6], (int)s[7]);
 #pragma unroll
-    for (int i = 8; i < 128; i += 8) {
+    for (int i = 8; i < kHN; i += 8) {
       m0 = max(max(m0, (int)s[i + 0]), (int)s[i + 1]);
       m1 = max(max(m1, (int)s[i + 2]), (int)s[i + 3]);
       m2 = max(max(m2, (int)s[i + 4]), (int)s[i + 5]);
@@ -122,7 +131,7 @@ __device__ __forceinline__ float tile_row_max(uint32_t (&s)[128], float c, int n
   } else {
     if constexpr (kMasked) {
 #pragma unroll
-      for (int i = 0; i < 128; ++i)
+      for (int i = 0; i < kHN; ++i)
         if (i >= n_valid) s[i] = 0xFF800000u;  // -inf
     }
     float m0 = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1]));
@@ -130,7 +139,7 @@ __device__ __forceinline__ float tile_row_max(uint32_t (&s)[128], float c, int n
     float m2 = fmaxf(__uint_as_float(s[4]), __uint_as_float(s[5]));
     float m3 = fmaxf(__uint_as_float(s[6]), __uint_as_float(s[7]));
 #pragma unroll
-    for (int i = 8; i < 128; i += 8) {
+    for (int i = 8; i < kHN; i += 8) {
       m0 = fmaxf(fmaxf(m0, __uint_as_float(s[i + 0])), __uint_as_float(s[i + 1]));
       m1 = fmaxf(fmaxf(m1, __uint_as_float(s[i + 2])), __uint_as_float(s[i + 3]));
       m2 = fmaxf(fmaxf(m2, __uint_as_float(s[i + 4])), __uint_as_float(s[i + 5]));
@@ -140,44 +149,111 @@ __device__ __forceinline__ float tile_row_max(uint32_t (&s)[128], float c, int n
   }
 }
 
-template <bool kInt8, bool kFastExp, bool kMasked>
-__device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[128], uint32_t (&p)[64], float c,
-                                             float m_used, int n_valid, float& l0, float& l1) {
+// Packed fp32x2 helpers (FFMA2 / FADD2 / FMUL2: two lanes of fp32 per instruction on sm_100).
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// 2^x for a pair on the FMA pipe instead of the MUFU (the SFU is the scarcest unit of this
+// kernel: 16 exp2/clk/SM).  Cody-Waite split x = n + f with n = floor(x) taken by a round-down
+// add of 1.5*2^23, 2^f by a degree-3 minimax polynomial on [0,1) (max rel. error 9e-5, far
+// below the fp16 rounding of P), 2^n by adding n to the exponent field.
+__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& e0, float& e1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t x = pack2(x0, x1);
+  const uint64_t magic = pack2(kMagicF, kMagicF);
+  const uint64_t xr = fadd2_rm(x, magic);           // mantissa low bits = floor(x)
+  const uint64_t f = fsub2(x, fsub2(xr, magic));    // f in [0,1)
+  uint64_t pl = ffma2(pack2(0.077119089663028717f, 0.077119089663028717f), f,
+                      pack2(0.227564394474029541f, 0.227564394474029541f));
+  pl = ffma2(pl, f, pack2(0.695146143436431885f, 0.695146143436431885f));
+  pl = ffma2(pl, f, pack2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack2(pl, p0, p1);
+  unpack2(xr, r0, r1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+
+// kPolyEvery: every kPolyEvery-th pair of the row takes the polynomial path (0 = all on MUFU).
+template <bool kInt8, bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2>
+__device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t (&p)[kHN / 2],
+                                             float c, float m_used, int n_valid,
+                                             uint64_t (&lsum)[2]) {
   // x = s*c - m_used.  INT8: s is an int32 with |s| < 2^22, so bits(s + 0x4B400000) is the
   // float 12582912 + s exactly and one FMA does int->float, scale and max subtraction.
   const float bias = kInt8 ? -fmaf(kMagicF, c, m_used) : -m_used;
+  const uint64_t c2 = pack2(c, c), bias2 = pack2(bias, bias);
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    float x0, x1;
+  for (int i = kBegin; i < kEnd; ++i) {
+    float f0, f1;
     if constexpr (kInt8) {
-      x0 = fmaf(__int_as_float((int)s[2 * i] + kMagicI2F), c, bias);
-      x1 = fmaf(__int_as_float((int)s[2 * i + 1] + kMagicI2F), c, bias);
+      f0 = __int_as_float((int)s[2 * i] + kMagicI2F);
+      f1 = __int_as_float((int)s[2 * i + 1] + kMagicI2F);
     } else {
-      x0 = fmaf(__uint_as_float(s[2 * i]), c, bias);
-      x1 = fmaf(__uint_as_float(s[2 * i + 1]), c, bias);
+      f0 = __uint_as_float(s[2 * i]);
+      f1 = __uint_as_float(s[2 * i + 1]);
     }
-    if constexpr (kFastExp) {
-      uint32_t e = ex2_f16x2(pack_f16x2(x0, x1));
-      if constexpr (kMasked) {
-        if (2 * i >= n_valid) e &= 0xFFFF0000u;
-        if (2 * i + 1 >= n_valid) e &= 0x0000FFFFu;
-      }
-      add_f16x2_to_f32(l0, l1, e);
-      p[i] = e;
+    float x0, x1, e0, e1;
+    unpack2(ffma2(pack2(f0, f1), c2, bias2), x0, x1);
+    if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery > 0 ? kPolyEvery : 1) - 1) {
+      exp2_poly_pair(x0, x1, e0, e1);
     } else {
-      float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-      if constexpr (kMasked) {
-        if (2 * i >= n_valid) e0 = 0.f;
-        if (2 * i + 1 >= n_valid) e1 = 0.f;
-      }
-      l0 += e0;
-      l1 += e1;
-      p[i] = pack_f16x2(e0, e1);
+      e0 = ex2_approx(x0);
+      e1 = ex2_approx(x1);
     }
+    if constexpr (kMasked) {
+      if (2 * i >= n_valid) e0 = 0.f;
+      if (2 * i + 1 >= n_valid) e1 = 0.f;
+    }
+    lsum[i & 1] = fadd2(lsum[i & 1], pack2(e0, e1));
+    p[i] = pack_f16x2(e0, e1);
   }
 }
 
-template <bool kInt8, int kD, bool kFastExp>
+// Named barriers 1/2 keep the two softmax warpgroups half a step out of phase (kStagger): tile 1
+// starts step i only once tile 0 is midway through its step i, and tile 0 starts step i+1 only
+// once tile 1 is midway through step i.  One warpgroup's barrier/TMEM/max overhead then overlaps
+// the other's MUFU-bound exponentials instead of both idling the MUFU at the same time.
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool kInt8, int kD, int kPolyEvery, bool kStagger, bool kPipe, bool kTrace>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, AttnParams prm) {
@@ -213,9 +289,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&bars->v_empty[i], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&bars->s_full[t], 1);
-      mbar_init(&bars->p_full[t], 128);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars->s_full[t][b], 1);
+        mbar_init(&bars->p_full[t][b], 128);
+      }
       mbar_init(&bars->pv_done[t], 1);
+      mbar_init(&bars->o_final[t], 1);
     }
     fence_mbar_init();
   }
@@ -264,69 +343,95 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
    } else if (warp == kMmaWarp) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this code with uniform control flow (so descriptors live in uniform
+    // registers); only the tcgen05.mma / tcgen05.commit instructions are issued by one elected
+    // lane.  Issuing from inside a divergent `if (lane == 0)` costs ~100 clk per MMA.
+    {
       const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
-      auto issue_qk = [&](int t, int st) {
-        const uint32_t d_tmem = tmem_base + (t ? kColS1 : kColS0);
+      const bool leader = elect_one() != 0;
+      // S_t[buf] = Q_t · K(stage st, key half `half`)^T
+      auto issue_qk = [&](int t, int buf, int st, int half) {
+        const uint32_t d_tmem = tmem_base + (t ? kColS1 : kColS0) + buf * kHN;
 #pragma unroll
         for (int ks = 0; ks < C::kStepsQK; ++ks) {
           const uint32_t off = (uint32_t)((ks * 32) / C::kAtomQK) * C::kSubBytesQK +
                                (uint32_t)((ks * 32) % C::kAtomQK);
           const uint64_t a = make_smem_desc(sQ_a + t * C::kTileBytesQK + off, C::kAtomQK);
-          const uint64_t b = make_smem_desc(sK_a + st * C::kTileBytesQK + off, C::kAtomQK);
-          if constexpr (kInt8) mma_i8_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
-          else mma_f16_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
+          const uint64_t b = make_smem_desc(
+              sK_a + st * C::kTileBytesQK + off + half * C::kHalfBytesQK, C::kAtomQK);
+          if (leader) {
+            if constexpr (kInt8) mma_i8_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
+            else mma_f16_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
+          }
         }
       };
-      auto issue_pv = [&](int t, int st, bool accumulate) {
+      // O_t (+)= P_t[buf] · V(stage st, key half `half`)
+      auto issue_pv = [&](int t, int buf, int st, int half, bool accumulate) {
         const uint32_t d_tmem = tmem_base + (t ? kColO1 : kColO0);
-        const uint32_t p_tmem = tmem_base + (t ? kColS1 : kColS0);
+        const uint32_t p_tmem = tmem_base + (t ? kColS1 : kColS0) + buf * kHN;
 #pragma unroll
         for (int ks = 0; ks < C::kStepsPV; ++ks) {
-          const uint32_t off = (uint32_t)(ks / 4) * C::kSubBytesV + (uint32_t)(ks % 4) * 32;
+          const uint32_t off = (uint32_t)half * C::kSubBytesV + (uint32_t)ks * 32;
           const uint64_t b = make_smem_desc(sV_a + st * C::kTileBytesV + off, 128);
-          mma_f16_ts(d_tmem, p_tmem + ks * 8, b, C::kIdescPV, (accumulate || ks > 0) ? 1u : 0u);
+          if (leader) mma_f16_ts(d_tmem, p_tmem + ks * 8, b, C::kIdescPV, (accumulate || ks > 0) ? 1u : 0u);
         }
       };
 
+      auto commit = [&](uint64_t* bar) { if (leader) mma_commit(bar); };
+      const int n_half = prm.n_half_steps;
       mbar_wait(&bars->q_full, 0, err_flag, 201, dead);
       mbar_wait(&bars->k_full[0], 0, err_flag, 202, dead);
       tc_fence_after();
-      issue_qk(0, 0);
-      mma_commit(&bars->s_full[0]);
-      issue_qk(1, 0);
-      mma_commit(&bars->s_full[1]);
-      mma_commit(&bars->k_empty[0]);
+      __syncwarp();
+      // prologue: scores of half-steps 0 and 1 for both query tiles
+      for (int t = 0; t < 2; ++t)
+        for (int i = 0; i < 2 && i < n_half; ++i) {
+          issue_qk(t, i, 0, i);
+          commit(&bars->s_full[t][i]);
+        }
+      commit(&bars->k_empty[0]);
 
-      for (int j = 0; j < n_tiles; ++j) {
+      for (int i = 0; i < n_half; ++i) {
+        const int j = i >> 1, half = i & 1;
         const int st = j % C::kStages;
         const uint32_t ph = (uint32_t)(j / C::kStages) & 1;
-        const int jn = j + 1;
+        const uint32_t pbuf = (uint32_t)(i >> 1) & 1;   // parity of the [t][half] barriers
+        const int in = i + 2, jn = in >> 1;
         const int stn = jn % C::kStages;
         const uint32_t phn = (uint32_t)(jn / C::kStages) & 1;
-        const bool more = jn < n_tiles;
+        const bool more = in < n_half;
+        long long* trm = kTrace ? prm.trace + (size_t)2 * n_half * 4 + (size_t)i * 4 : nullptr;
+        const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
 
-        mbar_wait(&bars->v_full[st], ph, err_flag, 203, dead);
-        mbar_wait(&bars->p_full[0], j & 1, err_flag, 204, dead);
+        if (half == 0) mbar_wait(&bars->v_full[st], ph, err_flag, 203, dead);
+        mbar_wait(&bars->p_full[0][half], pbuf, err_flag, 204, dead);
         tc_fence_after();
-        issue_pv(0, st, j > 0);
-        mma_commit(&bars->pv_done[0]);
+        if (tracer) trm[0] = clock64();
+        issue_pv(0, half, st, half, i > 0);
+        commit(&bars->pv_done[0]);
+        if (i == n_half - 1) commit(&bars->o_final[0]);
         if (more) {
-          mbar_wait(&bars->k_full[stn], phn, err_flag, 205, dead);
-          tc_fence_after();
-          issue_qk(0, stn);
-          mma_commit(&bars->s_full[0]);
+          if (half == 0) {
+            mbar_wait(&bars->k_full[stn], phn, err_flag, 205, dead);
+            tc_fence_after();
+          }
+          issue_qk(0, half, stn, half);
+          commit(&bars->s_full[0][half]);
         }
-        mbar_wait(&bars->p_full[1], j & 1, err_flag, 206, dead);
+        if (tracer) trm[1] = clock64();
+        mbar_wait(&bars->p_full[1][half], pbuf, err_flag, 206, dead);
         tc_fence_after();
-        issue_pv(1, st, j > 0);
-        mma_commit(&bars->pv_done[1]);
-        mma_commit(&bars->v_empty[st]);
+        if (tracer) trm[2] = clock64();
+        issue_pv(1, half, st, half, i > 0);
+        commit(&bars->pv_done[1]);
+        if (i == n_half - 1) commit(&bars->o_final[1]);
+        if (half == 1 || i == n_half - 1) commit(&bars->v_empty[st]);
         if (more) {
-          issue_qk(1, stn);
-          mma_commit(&bars->s_full[1]);
-          mma_commit(&bars->k_empty[stn]);
+          issue_qk(1, half, stn, half);
+          commit(&bars->s_full[1][half]);
+          if (half == 1 || in == n_half - 1) commit(&bars->k_empty[stn]);
         }
+        if (tracer) trm[3] = clock64();
       }
     }
    }
@@ -349,33 +454,50 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 
     float m_used = -INFINITY;
-    float l0 = 0.f, l1 = 0.f;
+    uint64_t lsum[2] = {0ull, 0ull};  // four fp32 partial row sums (packed pairs)
+    const int n_half = prm.n_half_steps;
+    const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0;
+    long long* tr = kTrace ? prm.trace + (size_t)t * n_half * 4 : nullptr;
 
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&bars->s_full[t], j & 1, err_flag, 301 + t, dead);
+    // The softmax loop is software-pipelined over half-steps: while the exponentials of step i
+    // run, the scores of step i+1 (already computed by the tensor core: S is double-buffered)
+    // are fetched from TMEM and their row max is taken, so tcgen05.ld latency and the max
+    // dependency chain hide under the MUFU work.  Two register arrays (sA, sB) alternate.
+
+    auto turn_begin = [&](int i) {
+      if constexpr (kStagger) {
+        if (t == 1) named_bar_sync(1, 256);
+        else if (i > 0) named_bar_sync(2, 256);
+      }
+    };
+    auto turn_mid = [&](int i) {
+      if constexpr (kStagger) {
+        if (t == 0) named_bar_arrive(1, 256);
+        else if (i + 1 < n_half) named_bar_arrive(2, 256);
+      }
+    };
+    // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld)
+    auto fetch = [&](int i, uint32_t (&dst)[kHN]) {
+      const int buf = i & 1;
+      mbar_wait(&bars->s_full[t][buf], (uint32_t)(i >> 1) & 1, err_flag, 301 + t, dead);
       dead = __any_sync(0xffffffffu, dead);
       tc_fence_after();
-
-      uint32_t s[128];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) tmem_ld32(tS + i * 32, &s[i * 32]);
-      tmem_wait_ld();
-
-      const int n_valid = prm.N - j * kBN;  // keys of this tile that exist (>=1)
-      const bool masked = n_valid < kBN;
-      float mt = masked ? tile_row_max<kInt8, true>(s, c, n_valid)
-                        : tile_row_max<kInt8, false>(s, c, n_valid);
-
-      // Lazy max: keep the old reference max unless the new one is more than 2^kRescaleThreshold
-      // larger.  The decision is made warp-uniform because tcgen05.ld/st are warp collectives.
+      tmem_ld32(tS + buf * kHN, &dst[0]);
+      tmem_ld32(tS + buf * kHN + 32, &dst[32]);
+    };
+    // lazy max update (+ rare rescale of O and l) for step i given the step's row max `mt`.
+    // Keeps the old reference max unless the new one is more than 2^kRescaleThreshold larger.
+    // The decision is made warp-uniform because tcgen05.ld/st are warp collectives.
+    auto update_max = [&](int i, float mt) {
       const bool need = mt > m_used + kRescaleThreshold;
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? mt : m_used;
-        if (j > 0) {
+        if (i > 0) {
           const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
-          l0 *= alpha;
-          l1 *= alpha;
-          mbar_wait(&bars->pv_done[t], (j - 1) & 1, err_flag, 311 + t, dead);
+          const uint64_t alpha2 = pack2(alpha, alpha);
+          lsum[0] = fmul2(lsum[0], alpha2);
+          lsum[1] = fmul2(lsum[1], alpha2);
+          mbar_wait(&bars->pv_done[t], (i - 1) & 1, err_flag, 311 + t, dead);
           dead = __any_sync(0xffffffffu, dead);
           tc_fence_after();
 #pragma unroll
@@ -384,29 +506,109 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tmem_ld32(tO + ch * 32, o);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
             tmem_st32(tO + ch * 32, o);
           }
+          tmem_wait_st();
         }
         m_used = m_new;
       }
-
-      uint32_t p[64];
-      if (masked) tile_row_exp<kInt8, kFastExp, true>(s, p, c, m_used, n_valid, l0, l1);
-      else tile_row_exp<kInt8, kFastExp, false>(s, p, c, m_used, n_valid, l0, l1);
-
-      tmem_st32(tS, &p[0]);
-      tmem_st32(tS + 32, &p[32]);
+    };
+    // P_t(i) -> TMEM (over the S buffer it came from), then tell the MMA warp.
+    auto publish = [&](int i, const uint32_t (&p)[kHN / 2]) {
+      const int buf = i & 1;
+      tmem_st32(tS + buf * kHN, &p[0]);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->p_full[t]);
+      mbar_arrive(&bars->p_full[t][buf]);
+      if (tracer) tr[i * 4 + 3] = clock64();
+    };
+    // pipelined step: exp of `cur` (step i, unmasked) overlapped with fetch + max of step i+1.
+    auto pipe_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur, uint32_t (&nxt)[kHN], float& mt_nxt) {
+      turn_begin(i);
+      if (tracer) tr[i * 4 + 0] = clock64();
+      update_max(i, mt_cur);
+      uint32_t p[kHN / 2];
+      // S_t(i+1) is issued behind P·V of step i-1, i.e. it lands roughly a third of the way into
+      // this step: run part of the exponentials first so the fetch does not stall on it.
+      tile_row_exp<kInt8, false, kPolyEvery, 0, 12>(cur, p, c, m_used, kHN, lsum);
+      fetch(i + 1, nxt);
+      turn_mid(i);
+      tile_row_exp<kInt8, false, kPolyEvery, 12, 22>(cur, p, c, m_used, kHN, lsum);
+      tmem_wait_ld();
+      mt_nxt = tile_row_max<kInt8, false>(nxt, c, kHN);
+      tile_row_exp<kInt8, false, kPolyEvery, 22, kHN / 2>(cur, p, c, m_used, kHN, lsum);
+      if (tracer) tr[i * 4 + 2] = clock64();
+      publish(i, p);
+    };
+    // step whose scores are already in registers, nothing left to prefetch (unmasked).
+    auto drain_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur) {
+      turn_begin(i);
+      if (tracer) tr[i * 4 + 0] = clock64();
+      update_max(i, mt_cur);
+      turn_mid(i);
+      uint32_t p[kHN / 2];
+      tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum);
+      if (tracer) tr[i * 4 + 2] = clock64();
+      publish(i, p);
+    };
+
+    uint32_t sA[kHN], sB[kHN];
+    float mtA = 0.f, mtB = 0.f;
+    int i = 0;
+    if (!kPipe) {
+      // plain (non-pipelined) order: fetch, wait, max, exp, publish for every full step
+      for (; i + 1 < n_half; ++i) {
+        fetch(i, sA);
+        tmem_wait_ld();
+        drain_step(i, sA, tile_row_max<kInt8, false>(sA, c, kHN));
+      }
+    } else if (n_half >= 2) {
+      // steps 0 .. n_half-2 are full (unmasked) by construction; only the last one can be ragged
+      fetch(0, sA);
+      tmem_wait_ld();
+      mtA = tile_row_max<kInt8, false>(sA, c, kHN);
+      bool in_a = true;
+      while (i + 2 < n_half) {
+        pipe_step(i, sA, mtA, sB, mtB);
+        ++i;
+        if (!(i + 2 < n_half)) { in_a = false; break; }
+        pipe_step(i, sB, mtB, sA, mtA);
+        ++i;
+      }
+      if (in_a) drain_step(i, sA, mtA);
+      else drain_step(i, sB, mtB);
+      ++i;
+    }
+    {
+      // last step (i == n_half-1): may cover fewer than 64 existing keys
+      turn_begin(i);
+      turn_mid(i);
+      if (tracer) tr[i * 4 + 0] = clock64();
+      fetch(i, sA);
+      tmem_wait_ld();
+      const int n_valid = prm.N - i * kHN;  // >= 1
+      uint32_t p[kHN / 2];
+      if (n_valid < kHN) {
+        update_max(i, tile_row_max<kInt8, true>(sA, c, n_valid));
+        tile_row_exp<kInt8, true, kPolyEvery>(sA, p, c, m_used, n_valid, lsum);
+      } else {
+        update_max(i, tile_row_max<kInt8, false>(sA, c, kHN));
+        tile_row_exp<kInt8, false, kPolyEvery>(sA, p, c, m_used, kHN, lsum);
+      }
+      if (tracer) tr[i * 4 + 2] = clock64();
+      publish(i, p);
     }
 
     // ---------------------------------------------------------------- epilogue: O * sV / l
-    mbar_wait(&bars->pv_done[t], (n_tiles - 1) & 1, err_flag, 321 + t, dead);
+    // (a parity wait on pv_done could alias here: the barrier may be two phases behind)
+    mbar_wait(&bars->o_final[t], 0, err_flag, 321 + t, dead);
     dead = __any_sync(0xffffffffu, dead);
     tc_fence_after();
-    const float l = l0 + l1;
+    float l, la, lb, lc, ld;
+    unpack2(lsum[0], la, lb);
+    unpack2(lsum[1], lc, ld);
+    l = (la + lb) + (lc + ld);
     const float inv = (l > 0.f) ? out_scale / l : 0.f;  // fa_tc_int8_b.cu:549-553 guard
     const int row = q_base + t * kBM + row_in_tile;
     const int b = unit / prm.H, head = unit % prm.H;
@@ -493,7 +695,7 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
   return true;
 }
 
-template <bool kInt8, int kD, bool kFastExp>
+template <bool kInt8, int kD, int kPolyEvery, bool kStagger, bool kPipe, bool kTrace>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD>;
   const uint64_t units = (uint64_t)a.B * a.H;
@@ -502,7 +704,7 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
       !make_map_2d(&tk, a.Kp, C::kEltQK, units * a.n_pad, kD, kBN, C::kAtomQK / C::kEltQK, err) ||
       !make_map_2d(&tv, a.Vt, 2, units * kD, a.n_pad, kD, 64, err))
     return false;
-  auto kern = attn_fwd_kernel<kInt8, kD, kFastExp>;
+  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kStagger, kPipe, kTrace>;
   {  // per device (context) attribute; cheap enough to set on every launch
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
@@ -512,10 +714,12 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.O = a.O;
   p.scales = a.scales;
   p.error_flag = a.error_flag;
+  p.trace = a.trace;
   p.B = a.B; p.N = a.N; p.H = a.H; p.d = a.d;
   p.n_pad = a.n_pad;
   p.units = (int)units;
   p.n_kv_tiles = (a.N + kBN - 1) / kBN;
+  p.n_half_steps = (a.N + kHN - 1) / kHN;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)a.d);
   dim3 grid((a.N + 2 * kBM - 1) / (2 * kBM), (unsigned)units, 1);
   kern<<<grid, kThreads, C::kSmemBytes, a.stream>>>(tq, tk, tv, p);
@@ -528,20 +732,46 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
 
 bool launch_attention(const AttnLaunch& a, std::string* err) {
   if (a.units_y_limit_exceeded()) { *err = "B*h exceeds the CUDA grid.y limit (65535)"; return false; }
+  // a.variant = k + 100*s + 1000*n: exp2 of every k-th score pair goes to the FMA-pipe polynomial
+  // (0 = all MUFU); s = 1 staggers the two softmax warpgroups by half a step; n = 1 disables the
+  // software pipelining of the softmax loop.
+  const int poly = a.variant % 100;
+  const bool stagger = (a.variant / 100) % 10 != 0;
+  const bool pipe = (a.variant / 1000) % 10 == 0;
+  if (a.trace) {
+    if (!(a.int8 && a.d_pad == 128)) { *err = "tracing is only built for the INT8 d=128 kernel"; return false; }
+    return pipe ? launch_cfg<true, 128, 0, false, true, true>(a, err) : launch_cfg<true, 128, 0, false, false, true>(a, err);
+  }
+#define QMHA_DISPATCH(INT8, D)                                                      \
+  if (stagger) {                                                                    \
+    if (poly == 0 && pipe) return launch_cfg<INT8, D, 0, true, true, false>(a, err); \
+  } else if (pipe) {                                                                \
+    switch (poly) {                                                                 \
+      case 0: return launch_cfg<INT8, D, 0, false, true, false>(a, err);            \
+      case 4: return launch_cfg<INT8, D, 4, false, true, false>(a, err);            \
+      case 8: return launch_cfg<INT8, D, 8, false, true, false>(a, err);            \
+    }                                                                               \
+  } else {                                                                          \
+    switch (poly) {                                                                 \
+      case 0: return launch_cfg<INT8, D, 0, false, false, false>(a, err);           \
+      case 8: return launch_cfg<INT8, D, 8, false, false, false>(a, err);           \
+    }                                                                               \
+  }
   if (a.int8) {
     switch (a.d_pad) {
-      case 32: return launch_cfg<true, 32, true>(a, err);
-      case 64: return launch_cfg<true, 64, true>(a, err);
-      case 128: return launch_cfg<true, 128, true>(a, err);
+      case 32: QMHA_DISPATCH(true, 32) break;
+      case 64: QMHA_DISPATCH(true, 64) break;
+      case 128: QMHA_DISPATCH(true, 128) break;
     }
   } else {
     switch (a.d_pad) {
-      case 32: return launch_cfg<false, 32, false>(a, err);
-      case 64: return launch_cfg<false, 64, false>(a, err);
-      case 128: return launch_cfg<false, 128, false>(a, err);
+      case 32: QMHA_DISPATCH(false, 32) break;
+      case 64: QMHA_DISPATCH(false, 64) break;
+      case 128: QMHA_DISPATCH(false, 128) break;
     }
   }
-  *err = "unsupported padded head dimension";
+#undef QMHA_DISPATCH
+  *err = "unsupported padded head dimension or kernel variant";
   return false;
 }
 

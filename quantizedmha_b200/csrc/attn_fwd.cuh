@@ -10,10 +10,12 @@ struct AttnParams {
   float* O;             // [B, N, H*d] fp32
   const float* scales;  // [3, units] (INT8 variant) or nullptr
   int* error_flag;      // device int: 0 = ok, otherwise the wait site that timed out
+  long long* trace;     // debug timeline buffer [3 roles][n_half_steps][4] (traced build only)
   int B, N, H, d;
   int n_pad;            // padded sequence length of the prepared operands (multiple of 256)
   int units;            // B*H
-  int n_kv_tiles;       // ceil(N / 128)
+  int n_kv_tiles;       // ceil(N / 128): K/V tiles staged by TMA
+  int n_half_steps;     // ceil(N / 64): 64-key softmax/MMA half-steps
   float scale_log2;     // log2(e) / sqrt(d)
 };
 
@@ -24,6 +26,8 @@ struct AttnLaunch {
   const float* scales;
   float* O;
   int* error_flag;
+  long long* trace = nullptr;  // device buffer; non-null selects the traced instantiation
+  int variant = 0;             // k > 0: exp2 of every k-th score pair on the FMA-pipe polynomial
   int B, N, H, d, n_pad, d_pad;
   bool int8;
   cudaStream_t stream;
