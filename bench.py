@@ -77,12 +77,12 @@ def cpu_step(n, d, heads, threads):
 def cpu_baseline(args):
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, args.cpu_threads or cores))
-    heads = args.cpu_sample_heads or threads
+    heads = args.cpu_sample_heads or 16 * threads   # ~10-20 s of CPU work on the GPU box's cores
     n, d = args.cpu_sample_n, WORKLOADS[args.workload][3]
     sec, kind = cpu_step(n, d, heads, threads)
     flops = 4.0 * heads * n * n * d
     return {"value": flops / sec / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": kind,
-            "sample": f"{heads} heads of the workload truncated to N={n}, d={d}; one head per thread; "
+            "sample": f"{heads} heads of the workload truncated to N={n}, d={d}; {threads} threads, one head at a time each; "
                       f"{sec:.2f} s; reference cpu_mha (tests/generate_golden.cpp:53-92)"}
 
 
@@ -93,7 +93,7 @@ def run_reference(args):
     B, H, N, d, kernel, scaling = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, args.cpu_threads or cores))
-    heads = args.cpu_sample_heads or threads
+    heads = args.cpu_sample_heads or 4 * threads   # a few seconds per step: K+W steps stay within minutes
     n = args.cpu_sample_n
     kind = "port"
     for _ in range(args.warmup):
@@ -112,7 +112,7 @@ def run_reference(args):
         "config": {"workload": f"{args.workload}: B={B} H={H} N={N} d={d}; CPU step = bounded sample of "
                                f"{heads} heads truncated to N={n}"},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": kind,
-                         "sample": f"{heads} heads, N={n}, d={d}, one head per thread"},
+                         "sample": f"{heads} heads, N={n}, d={d}, {threads} threads, one head at a time each"},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
