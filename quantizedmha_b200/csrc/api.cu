@@ -156,6 +156,14 @@ int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, i
   if (a.int8) {
     if (gran != QMHA_GRAN_TENSOR && gran != QMHA_GRAN_HEAD)
       return fail("the attention path supports QMHA_GRAN_TENSOR and QMHA_GRAN_HEAD scales");
+    // Per-(batch, head) scales: one cluster kernel reads the inputs from HBM once.  Per-tensor
+    // scales need a global maximum first and keep the two-pass path (as does an odd head dim).
+    static const bool two_pass_env = getenv("QMHA_TWO_PASS_QUANT") != nullptr;
+    if (gran == QMHA_GRAN_HEAD && (d & 3) == 0 && !two_pass_env) {
+      if ((e = qmha::launch_fused_quantize(a)) != cudaSuccess) return fail_cuda("fused quantise launch", e);
+      g_launches += 1;
+      return 0;
+    }
     if ((e = qmha::launch_absmax_and_scales(a, amax, gran == QMHA_GRAN_TENSOR)) != cudaSuccess)
       return fail_cuda("absmax launch", e);
     g_launches += 2;

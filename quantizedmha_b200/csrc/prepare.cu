@@ -17,6 +17,7 @@
 //           prepare_kernel -> quantise/convert + re-layout (+ transpose of V through smem)
 //           quantize_blocks_kernel / quantize_static_kernel -> reference-granularity and
 //           golden-spec (generate_golden.cpp:94-101) quantisers in the input layout.
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
 #include "prepare.cuh"
@@ -235,6 +236,155 @@ __global__ void quantize_static_kernel(const float* __restrict__ X, int8_t* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused_quantize_kernel: absmax + quantise + re-layout of one (batch, head, tensor) slab by ONE
+// thread-block cluster, so the inputs cross HBM once.
+//   phase 1: every CTA of the cluster reduces max|x| over its share of the slab's rows,
+//            the cluster combines the CTA maxima through distributed shared memory;
+//   phase 2: every CTA re-reads its rows (now L2 resident: one CTA per SM keeps the live slabs
+//            of all clusters at ~64 MB of the 126 MB L2) and writes the prepared operands.
+// grid = (kClusterSize, B*H, 3), cluster = (kClusterSize,1,1), 1024 threads, 1 CTA/SM (the dynamic
+// shared-memory request is sized to forbid a second CTA).
+constexpr int kClusterSize = 8;
+constexpr int kFusedThreads = 1024;
+constexpr int kFusedSmemBytes = 120 * 1024;
+
+template <int kD>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kFusedThreads, 1)
+fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                      const float* __restrict__ V, float* __restrict__ scales,
+                      int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
+                      int N, int H, int d, int n_pad) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) uint8_t fused_smem[];
+  __shared__ float s_warp_max[kFusedThreads / 32];
+  __shared__ float s_cta_max;
+
+  const int z = blockIdx.z, unit = blockIdx.y;
+  const int b = unit / H, head = unit % H;
+  const int rank = (int)cluster.block_rank();
+  const float* X = z == 0 ? Q : (z == 1 ? K : V);
+  const int d_model = H * d;
+  const float* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+
+  // rows of this CTA: a multiple of 128 so V tiles never straddle CTAs
+  const int rows_per_cta = ((n_pad / 128 + kClusterSize - 1) / kClusterSize) * 128;
+  const int r_begin = rank * rows_per_cta;
+  const int r_end = min(n_pad, r_begin + rows_per_cta);
+
+  constexpr int kVecPerRow = kD / 4;                      // float4 slots per padded row
+  constexpr int kRowsPerPass = kFusedThreads / kVecPerRow;
+  const int vec = threadIdx.x % kVecPerRow;
+  const int rsub = threadIdx.x / kVecPerRow;
+  const bool col_ok = vec * 4 < d;                        // (d % 4 == 0 is required by the host)
+
+  // ---- phase 1: absmax over my rows
+  float m = 0.f;
+  if (col_ok) {
+    const float* col = src + vec * 4;
+    int r = r_begin + rsub;
+    const int r_stop = min(r_end, N);
+    for (; r + 7 * kRowsPerPass < r_stop; r += 8 * kRowsPerPass) {
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = ldg_f4(col + (size_t)(r + u * kRowsPerPass) * d_model);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m = absmax4(m, x[u]);
+    }
+    for (; r < r_stop; r += kRowsPerPass) m = absmax4(m, ldg_f4(col + (size_t)r * d_model));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) s_warp_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float w = s_warp_max[threadIdx.x];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, off));
+    if (threadIdx.x == 0) s_cta_max = w;
+  }
+  cluster.sync();
+  float amax = 0.f;
+#pragma unroll
+  for (int rk = 0; rk < kClusterSize; ++rk) amax = fmaxf(amax, *cluster.map_shared_rank(&s_cta_max, rk));
+  cluster.sync();  // nobody may leave (or reuse s_cta_max) while peers still read it
+
+  const float sc = fmaxf(amax / 127.0f, 1e-8f);  // fa_tc_int8_b.cu:104
+  const float inv_sc = 1.0f / sc;                // fa_tc_int8_b.cu:106
+  if (rank == 0 && threadIdx.x == 0) scales[(size_t)z * gridDim.y + unit] = sc;
+
+  // ---- phase 2: quantise + re-layout my rows
+  auto load4 = [&](int n, float (&x)[4]) {
+    x[0] = x[1] = x[2] = x[3] = 0.f;
+    if (n < N && col_ok) {
+      float4 v = ldg_f4(src + (size_t)n * d_model + vec * 4);
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+  };
+  if (z < 2) {
+    int8_t* dst = z == 0 ? Qp : Kp;
+    // 8 independent 16-byte loads in flight per thread (the re-read mostly hits L2)
+    for (int n = r_begin + rsub; n < r_end; n += 8 * kRowsPerPass) {
+      float x[8][4];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) load4(n + u * kRowsPerPass, x[u]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int nn = n + u * kRowsPerPass;
+        if (nn < r_end) {
+          const int q0 = quant1(x[u][0], inv_sc), q1 = quant1(x[u][1], inv_sc);
+          const int q2 = quant1(x[u][2], inv_sc), q3 = quant1(x[u][3], inv_sc);
+          const uint32_t pk = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) |
+                              ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+          *reinterpret_cast<uint32_t*>(dst + ((size_t)unit * n_pad + nn) * kD + vec * 4) = pk;
+        }
+      }
+    }
+  } else {
+    constexpr int kStride = kD + 2;  // halves; odd word stride spreads the transposed reads
+    constexpr int kLoads = 128 / kRowsPerPass;            // float4 loads per thread per 128-row tile
+    __half* tiles = reinterpret_cast<__half*>(fused_smem);  // 2 x [128][kStride], double buffered
+    float x[kLoads][4];
+    auto load_tile = [&](int n0) {
+#pragma unroll
+      for (int u = 0; u < kLoads; ++u) load4(n0 + rsub + u * kRowsPerPass, x[u]);
+    };
+    if (r_begin < r_end) load_tile(r_begin);
+    int buf = 0;
+    for (int n0 = r_begin; n0 < r_end; n0 += 128, buf ^= 1) {
+      __half* tile = tiles + buf * (128 * kStride);
+#pragma unroll
+      for (int u = 0; u < kLoads; ++u) {
+        const int r = rsub + u * kRowsPerPass;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          tile[r * kStride + vec * 4 + e] = __float2half_rn((float)quant1(x[u][e], inv_sc));
+      }
+      if (n0 + 128 < r_end) load_tile(n0 + 128);  // next tile's loads fly during the transposed writes
+      __syncthreads();
+      const int kp = threadIdx.x & 63;  // 2 consecutive keys per thread, 64 threads per d-row
+      for (int dd = threadIdx.x >> 6; dd < kD; dd += kFusedThreads / 64) {
+        __half2 o2 = __halves2half2(tile[(2 * kp) * kStride + dd], tile[(2 * kp + 1) * kStride + dd]);
+        *reinterpret_cast<__half2*>(Vt + ((size_t)unit * kD + dd) * n_pad + n0 + 2 * kp) = o2;
+      }
+      // (the other buffer is written next; this one is rewritten two tiles later, after a sync)
+    }
+  }
+}
+
+template <int kD>
+cudaError_t launch_fused_cfg(const PrepareArgs& a) {
+  auto kern = fused_quantize_kernel<kD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes);
+  if (e != cudaSuccess) return e;
+  dim3 grid(kClusterSize, a.B * a.H, 3);
+  kern<<<grid, kFusedThreads, kFusedSmemBytes, a.stream>>>(
+      a.Q, a.K, a.V, a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
+      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad);
+  return cudaGetLastError();
+}
+
 template <bool kInt8, int kD>
 cudaError_t launch_prepare_cfg(const PrepareArgs& a) {
   dim3 grid(a.n_pad / kPrepRows, a.B * a.H, 3);
@@ -256,6 +406,16 @@ cudaError_t launch_absmax_and_scales(const PrepareArgs& a, unsigned* amax_bits, 
   if (e != cudaSuccess) return e;
   finalize_scales_kernel<<<3, 256, 0, a.stream>>>(amax_bits, a.scales, units, per_tensor);
   return cudaGetLastError();
+}
+
+// Single-pass INT8 preparation with per-(batch, head) scales (requires d % 4 == 0).
+cudaError_t launch_fused_quantize(const PrepareArgs& a) {
+  switch (a.d_pad) {
+    case 32: return launch_fused_cfg<32>(a);
+    case 64: return launch_fused_cfg<64>(a);
+    case 128: return launch_fused_cfg<128>(a);
+  }
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_prepare(const PrepareArgs& a) {

@@ -20,6 +20,8 @@ struct PrepareArgs {
 
 // absmax pass + scale finalisation (3 launches incl. the memset node).
 cudaError_t launch_absmax_and_scales(const PrepareArgs& a, unsigned* amax_bits, int per_tensor);
+// absmax + quantise + re-layout in ONE launch (cluster kernel; INT8, per-(batch,head) scales, d%4==0).
+cudaError_t launch_fused_quantize(const PrepareArgs& a);
 // quantise / convert + re-layout (1 launch).
 cudaError_t launch_prepare(const PrepareArgs& a);
 cudaError_t launch_quantize_blocks(const float* X, int B, int N, int H, int d, int block_rows,
