@@ -242,18 +242,7 @@ __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t 
   }
 }
 
-// Named barriers 1/2 keep the two softmax warpgroups half a step out of phase (kStagger): tile 1
-// starts step i only once tile 0 is midway through its step i, and tile 0 starts step i+1 only
-// once tile 1 is midway through step i.  One warpgroup's barrier/TMEM/max overhead then overlaps
-// the other's MUFU-bound exponentials instead of both idling the MUFU at the same time.
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-template <bool kInt8, int kD, int kPolyEvery, bool kStagger, bool kPipe, bool kTrace>
+template <bool kInt8, int kD, int kPolyEvery, bool kTrace>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, AttnParams prm) {
@@ -464,18 +453,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // are fetched from TMEM and their row max is taken, so tcgen05.ld latency and the max
     // dependency chain hide under the MUFU work.  Two register arrays (sA, sB) alternate.
 
-    auto turn_begin = [&](int i) {
-      if constexpr (kStagger) {
-        if (t == 1) named_bar_sync(1, 256);
-        else if (i > 0) named_bar_sync(2, 256);
-      }
-    };
-    auto turn_mid = [&](int i) {
-      if constexpr (kStagger) {
-        if (t == 0) named_bar_arrive(1, 256);
-        else if (i + 1 < n_half) named_bar_arrive(2, 256);
-      }
-    };
     // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld)
     auto fetch = [&](int i, uint32_t (&dst)[kHN]) {
       const int buf = i & 1;
@@ -525,7 +502,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     };
     // pipelined step: exp of `cur` (step i, unmasked) overlapped with fetch + max of step i+1.
     auto pipe_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur, uint32_t (&nxt)[kHN], float& mt_nxt) {
-      turn_begin(i);
       if (tracer) tr[i * 4 + 0] = clock64();
       update_max(i, mt_cur);
       uint32_t p[kHN / 2];
@@ -533,7 +509,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // this step: run part of the exponentials first so the fetch does not stall on it.
       tile_row_exp<kInt8, false, kPolyEvery, 0, 12>(cur, p, c, m_used, kHN, lsum);
       fetch(i + 1, nxt);
-      turn_mid(i);
       tile_row_exp<kInt8, false, kPolyEvery, 12, 22>(cur, p, c, m_used, kHN, lsum);
       tmem_wait_ld();
       mt_nxt = tile_row_max<kInt8, false>(nxt, c, kHN);
@@ -543,10 +518,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     };
     // step whose scores are already in registers, nothing left to prefetch (unmasked).
     auto drain_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur) {
-      turn_begin(i);
       if (tracer) tr[i * 4 + 0] = clock64();
       update_max(i, mt_cur);
-      turn_mid(i);
       uint32_t p[kHN / 2];
       tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum);
       if (tracer) tr[i * 4 + 2] = clock64();
@@ -556,14 +529,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint32_t sA[kHN], sB[kHN];
     float mtA = 0.f, mtB = 0.f;
     int i = 0;
-    if (!kPipe) {
-      // plain (non-pipelined) order: fetch, wait, max, exp, publish for every full step
-      for (; i + 1 < n_half; ++i) {
-        fetch(i, sA);
-        tmem_wait_ld();
-        drain_step(i, sA, tile_row_max<kInt8, false>(sA, c, kHN));
-      }
-    } else if (n_half >= 2) {
+    if (n_half >= 2) {
       // steps 0 .. n_half-2 are full (unmasked) by construction; only the last one can be ragged
       fetch(0, sA);
       tmem_wait_ld();
@@ -582,8 +548,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     {
       // last step (i == n_half-1): may cover fewer than 64 existing keys
-      turn_begin(i);
-      turn_mid(i);
       if (tracer) tr[i * 4 + 0] = clock64();
       fetch(i, sA);
       tmem_wait_ld();
@@ -695,7 +659,7 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
   return true;
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kStagger, bool kPipe, bool kTrace>
+template <bool kInt8, int kD, int kPolyEvery, bool kTrace>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD>;
   const uint64_t units = (uint64_t)a.B * a.H;
@@ -704,7 +668,7 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
       !make_map_2d(&tk, a.Kp, C::kEltQK, units * a.n_pad, kD, kBN, C::kAtomQK / C::kEltQK, err) ||
       !make_map_2d(&tv, a.Vt, 2, units * kD, a.n_pad, kD, 64, err))
     return false;
-  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kStagger, kPipe, kTrace>;
+  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kTrace>;
   {  // per device (context) attribute; cheap enough to set on every launch
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
@@ -732,30 +696,17 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
 
 bool launch_attention(const AttnLaunch& a, std::string* err) {
   if (a.units_y_limit_exceeded()) { *err = "B*h exceeds the CUDA grid.y limit (65535)"; return false; }
-  // a.variant = k + 100*s + 1000*n: exp2 of every k-th score pair goes to the FMA-pipe polynomial
-  // (0 = all MUFU); s = 1 staggers the two softmax warpgroups by half a step; n = 1 disables the
-  // software pipelining of the softmax loop.
-  const int poly = a.variant % 100;
-  const bool stagger = (a.variant / 100) % 10 != 0;
-  const bool pipe = (a.variant / 1000) % 10 == 0;
+  // a.variant = k: exp2 of every k-th score pair goes to the FMA-pipe polynomial (0 = all MUFU)
+  const int poly = a.variant;
   if (a.trace) {
     if (!(a.int8 && a.d_pad == 128)) { *err = "tracing is only built for the INT8 d=128 kernel"; return false; }
-    return pipe ? launch_cfg<true, 128, 0, false, true, true>(a, err) : launch_cfg<true, 128, 0, false, false, true>(a, err);
+    return launch_cfg<true, 128, 0, true>(a, err);
   }
-#define QMHA_DISPATCH(INT8, D)                                                      \
-  if (stagger) {                                                                    \
-    if (poly == 0 && pipe) return launch_cfg<INT8, D, 0, true, true, false>(a, err); \
-  } else if (pipe) {                                                                \
-    switch (poly) {                                                                 \
-      case 0: return launch_cfg<INT8, D, 0, false, true, false>(a, err);            \
-      case 4: return launch_cfg<INT8, D, 4, false, true, false>(a, err);            \
-      case 8: return launch_cfg<INT8, D, 8, false, true, false>(a, err);            \
-    }                                                                               \
-  } else {                                                                          \
-    switch (poly) {                                                                 \
-      case 0: return launch_cfg<INT8, D, 0, false, false, false>(a, err);           \
-      case 8: return launch_cfg<INT8, D, 8, false, false, false>(a, err);           \
-    }                                                                               \
+#define QMHA_DISPATCH(INT8, D)                                   \
+  switch (poly) {                                                \
+    case 0: return launch_cfg<INT8, D, 0, false>(a, err);        \
+    case 4: return launch_cfg<INT8, D, 4, false>(a, err);        \
+    case 8: return launch_cfg<INT8, D, 8, false>(a, err);        \
   }
   if (a.int8) {
     switch (a.d_pad) {

@@ -19,7 +19,7 @@ import quantizedmha_b200 as qm  # noqa: E402
 OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 dev = torch.device("cuda:0")
-variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0,8,4,3,2".split(","))]
+variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0,8,4".split(","))]
 B, H, N, d = (int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "8,32,8192,128".split(",")))
 dm = H * d
 torch.manual_seed(1)
@@ -89,7 +89,7 @@ for kern in ("int8", "f16"):
         res.append(rec)
     if kern == "int8" and d == 128:
         nt = (N + 63) // 64
-        for v in (0, 1000):
+        for v in (0,):
             tr = np.zeros((3, nt, 4), np.int64)
             rc = L.qmha_debug_attention_trace(C.c_void_p(Qp.data_ptr()), C.c_void_p(Kp.data_ptr()), C.c_void_p(Vt.data_ptr()),
                                               C.c_void_p(sc.data_ptr()), C.c_void_p(out.data_ptr()), B, N, dm, H, v,
