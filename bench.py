@@ -209,7 +209,8 @@ def run_native(args):
     Qp = torch.empty((units, n_pad, d_pad), dtype=elt, device=dev)
     Kp = torch.empty_like(Qp)
     Vt = torch.empty((units, d_pad, n_pad), dtype=torch.float16, device=dev)
-    sc = torch.empty((3, units), dtype=torch.float32, device=dev)
+    gran = {"head": qm.GRAN_HEAD, "block": qm.GRAN_BLOCK, "tensor": qm.GRAN_TENSOR}[args.scales]
+    sc = torch.empty((3, units, n_pad // 32) if gran == qm.GRAN_BLOCK else (3, units), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream()
     sp = int(stream.cuda_stream)
 
@@ -219,7 +220,7 @@ def run_native(args):
 
     def prep():
         if kernel == "int8":
-            chk(L.qmha_quantize_qkv(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), Bl, N, dm, H, qm.GRAN_HEAD,
+            chk(L.qmha_quantize_qkv(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), Bl, N, dm, H, gran,
                                     Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), sc.data_ptr(), sp))
         else:
             chk(L.qmha_convert_qkv_f16(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), Bl, N, dm, H,
@@ -228,7 +229,7 @@ def run_native(args):
     def attn():
         chk(L.qmha_attention_prepared(Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(),
                                       sc.data_ptr() if kernel == "int8" else None, out.data_ptr(),
-                                      Bl, N, dm, H, kid, sp))
+                                      Bl, N, dm, H, kid, gran, sp))
 
     def barrier():
         if dist is not None:
@@ -269,11 +270,11 @@ def run_native(args):
     ho = torch.empty_like(hq, pin_memory=True)
     hq.copy_(tq); hk.copy_(tk); hv.copy_(tv)
     torch.cuda.synchronize()
-    chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Bl, N, dm, H, kid, qm.GRAN_HEAD))
+    chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Bl, N, dm, H, kid, gran))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Bl, N, dm, H, kid, qm.GRAN_HEAD))
+        chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Bl, N, dm, H, kid, gran))
     e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
     e2e_maxdiff = float((ho.to(dev) - out).abs().max().item())
 
@@ -297,7 +298,7 @@ def run_native(args):
         "dtype": "s8*s8->s32 (Q.K^T), f16*f16->f32 (P.V), f32 softmax" if kernel == "int8" else "f16*f16->f32, f32 softmax",
         "data": "synthetic U[0,1) (inputs/data.cu distribution), random on device",
         "config": {"workload": f"{args.workload}: B={B}{' per GPU' if scaling == 'weak' and world > 1 else ''} H={H} N={N} d={d} "
-                               f"kernel={kernel} scales=per-(batch,head)", "l2": "inputs (4.3 GB at c4) larger than the 126 MB L2",
+                               f"kernel={kernel} scales={args.scales}", "l2": "inputs (4.3 GB at c4) larger than the 126 MB L2",
                    "parallelism": f"(batch x head) units sharded over {world} GPU(s), no collective"},
         "attn_ms": attn_ms, "attn_tflops_per_gpu": attn_tflops, "prep_ms": prep_ms,
         "prep_gbs_algorithmic": prep_bytes / (prep_ms / 1e3) / 1e9, "prep_frac_of_hbm": prep_bytes / (prep_ms / 1e3) / 1e9 / pk["hbm"],
@@ -335,6 +336,8 @@ def main():
     ap.add_argument("--cpu-sample-heads", type=int, default=0, help="0 = one head per host thread")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scales", default="block", choices=["head", "block", "tensor"],
+                    help="granularity of the dynamic INT8 scales (block = the reference's 32-row tiles)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -30,7 +30,8 @@ Tensor flash_solve(const Tensor& Q, const Tensor& K, const Tensor& V, int64_t d_
   TORCH_CHECK(kid >= 0, "unknown kernel '", kernel, "'");
   const int rc = qmha_forward(Qc.data_ptr<float>(), Kc.data_ptr<float>(), Vc.data_ptr<float>(),
                               out.data_ptr<float>(), (int)B, (int)N, (int)d_model, (int)num_heads, kid,
-                              QMHA_GRAN_HEAD, at::cuda::getCurrentCUDAStream().stream());
+                              qmha_default_granularity((int)d_model, (int)num_heads),
+                              at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(rc == 0, qmha_last_error());
   return out;
 }

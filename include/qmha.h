@@ -36,8 +36,8 @@ extern "C" {
 /* Granularity of the dynamic INT8 scales (symmetric, zero-point free, fa_tc_int8_b.cu:104). */
 #define QMHA_GRAN_TENSOR 0 /* one scale per tensor                                   */
 #define QMHA_GRAN_HEAD 1   /* one scale per (batch, head) slab [N, d]  (default)     */
-#define QMHA_GRAN_BLOCK 2  /* one scale per (batch, head, 32-row block): reference granularity;
-                              supported by qmha_quantize_blocks only in this round       */
+#define QMHA_GRAN_BLOCK 2  /* one scale per (batch, head, 32-row block): the reference's own
+                              granularity (Br x d / Bc x d tiles); scales are [3, B*h, n_pad/32] */
 
 /* ---- the reference's own entry point -------------------------------------------------------
  * include/launchers.h:9-10.  Q,K,V,output: DEVICE pointers, fp32, contiguous row-major
@@ -67,7 +67,8 @@ int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, 
  *   Qp, Kp : [B*h, n_pad, d_pad]   int8 (INT8 variant) or fp16 (F16 variant), zero padded
  *   Vt     : [B*h, d_pad, n_pad]   fp16, TRANSPOSED (keys contiguous); for INT8 the values are
  *                                   the int8 codes stored exactly in fp16
- *   scales : [3, B*h] fp32 (Q, K, V) — for QMHA_GRAN_TENSOR every entry of a row is equal
+ *   scales : [3, B*h] fp32 (Q, K, V) — for QMHA_GRAN_TENSOR every entry of a row is equal;
+ *            [3, B*h, n_pad/32] for QMHA_GRAN_BLOCK
  * n_pad = N rounded up to 256, d_pad = 32/64/128 >= d. */
 int qmha_workspace_dims(int N, int d_model, int h, int* n_pad, int* d_pad);
 
@@ -97,7 +98,7 @@ int qmha_quantize_static(const float* X, int64_t n, float scale, float zero_poin
 /* ---- attention on prepared operands (kernel (b)/(c)) --------------------------------------- */
 int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt,
                             const float* scales, float* O, int B, int N, int d_model, int h,
-                            int kernel, void* stream);
+                            int kernel, int gran, void* stream);
 
 /* qmha_forward()/qmha_attention_prepared() are asynchronous; after synchronising the stream,
  * this reports (and clears) a device-side pipeline failure recorded by the kernel. */
@@ -114,6 +115,8 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
 const char* qmha_last_error(void);          /* "" when the last call on this thread succeeded */
 int qmha_set_kernel(const char* name);      /* default variant used by solve(); 0 = ok        */
 const char* qmha_get_kernel(void);          /* "int8" or "f16"                                */
+int qmha_default_granularity(int d_model, int h); /* what solve() uses: QMHA_GRAN_BLOCK when d%4==0
+                                                     (QMHA_SCALES=head|tensor overrides), else HEAD  */
 int qmha_kernel_from_name(const char* name); /* QMHA_KERNEL_* or -1                           */
 int64_t qmha_launch_count(void);            /* kernels launched by this library so far        */
 void qmha_shutdown(void);                   /* frees every per-device workspace               */

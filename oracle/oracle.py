@@ -44,6 +44,7 @@ class Oracle:
         L.oracle_quantize_dynamic.restype = C.c_int64
         L.oracle_quantize_static.argtypes = [_f32p, C.c_int64, C.c_float, C.c_float, _i8p]
         L.oracle_mha_int8_emulated.argtypes = [_i8p, _i8p, _i8p, _f32p, _f32p, _f32p, _f32p] + [C.c_int] * 6
+        L.oracle_mha_int8_emulated_block.argtypes = [_i8p, _i8p, _i8p, _f32p, _f32p, _f32p, _f32p] + [C.c_int] * 7
         L.oracle_save_reference.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int]
         L.oracle_save_reference.restype = C.c_int
         L.oracle_load_reference.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int]
@@ -128,6 +129,20 @@ class Oracle:
         o = np.empty(qq.shape, np.float32)
         self.lib.oracle_mha_int8_emulated(qq, kq, vq, sq, sk, sv, o, B, N, d_model, h,
                                           1 if p_format == "f16" else 0, threads)
+        return o
+
+    def mha_int8_emulated_block(self, qq, kq, vq, sq, sk, sv, h: int, block_rows: int = 32,
+                                p_format: str = "f16", threads: int = 0):
+        """Same with the reference's per-(head, 32-row block) scales; scales are [B*h*nblk]."""
+        qq, kq, vq = (np.ascontiguousarray(a, np.int8) for a in (qq, kq, vq))
+        sq, sk, sv = (np.ascontiguousarray(a, np.float32).ravel() for a in (sq, sk, sv))
+        B = 1 if qq.ndim == 2 else qq.shape[0]
+        N, d_model = qq.shape[-2], qq.shape[-1]
+        nblk = -(-N // block_rows)
+        assert sq.size == B * h * nblk and sk.size == sq.size and sv.size == sq.size
+        o = np.empty(qq.shape, np.float32)
+        self.lib.oracle_mha_int8_emulated_block(qq, kq, vq, sq, sk, sv, o, B, N, d_model, h, block_rows,
+                                                1 if p_format == "f16" else 0, threads)
         return o
 
     def num_threads(self) -> int:

@@ -366,6 +366,59 @@ void oracle_mha_int8_emulated(const int8_t* Qq, const int8_t* Kq, const int8_t* 
   });
 }
 
+// Same emulation with the reference's granularity: one scale per (batch, head, block of
+// `block_rows` rows) for Q, K and V (fa_tc_int8_b.cu:484,496,518); sQ/sK/sV have
+// B*h*ceil(N/block_rows) entries laid out [unit][block].
+void oracle_mha_int8_emulated_block(const int8_t* Qq, const int8_t* Kq, const int8_t* Vq,
+                                    const float* sQ, const float* sK, const float* sV, float* O,
+                                    int B, int N, int d_model, int h, int block_rows, int p_format,
+                                    int nthreads) {
+  const int d = d_model / h;
+  const double inv_sqrt_d = 1.0 / std::sqrt((double)d);
+  const int units = B * h;
+  const int nblk = (N + block_rows - 1) / block_rows;
+  run_parallel(nthreads, units, [&](int u) {
+    const int b = u / h, head = u % h, col = head * d;
+    const int8_t* Qb = Qq + (int64_t)b * N * d_model;
+    const int8_t* Kb = Kq + (int64_t)b * N * d_model;
+    const int8_t* Vb = Vq + (int64_t)b * N * d_model;
+    float* Ob = O + (int64_t)b * N * d_model;
+    const float* sq = sQ + (int64_t)u * nblk;
+    const float* sk = sK + (int64_t)u * nblk;
+    const float* sv = sV + (int64_t)u * nblk;
+    std::vector<int32_t> kT((size_t)d * N);
+    for (int j = 0; j < N; ++j)
+      for (int dd = 0; dd < d; ++dd) kT[(size_t)dd * N + j] = Kb[(int64_t)j * d_model + col + dd];
+    std::vector<int32_t> s(N);
+    std::vector<double> x(N), o(d);
+    for (int i = 0; i < N; ++i) {
+      std::fill(s.begin(), s.end(), 0);
+      for (int dd = 0; dd < d; ++dd) {
+        const int32_t qv = Qb[(int64_t)i * d_model + col + dd];
+        const int32_t* kr = &kT[(size_t)dd * N];
+        for (int j = 0; j < N; ++j) s[j] += qv * kr[j];
+      }
+      const double cq = (double)sq[i / block_rows] * inv_sqrt_d;
+      double mx = -INFINITY;
+      for (int j = 0; j < N; ++j) {
+        x[j] = (double)s[j] * cq * (double)sk[j / block_rows];
+        mx = std::max(mx, x[j]);
+      }
+      double sum = 0.0;
+      std::fill(o.begin(), o.end(), 0.0);
+      for (int j = 0; j < N; ++j) {
+        double e = std::exp(x[j] - mx);
+        if (p_format == 1) e = (double)round_to_f16((float)e);
+        sum += e;
+        const double w = e * (double)sv[j / block_rows];
+        const int8_t* v = Vb + (int64_t)j * d_model + col;
+        for (int cc = 0; cc < d; ++cc) o[cc] += w * (double)v[cc];
+      }
+      for (int cc = 0; cc < d; ++cc) Ob[(int64_t)i * d_model + col + cc] = (float)(o[cc] / sum);
+    }
+  });
+}
+
 }  // extern "C"
 
 // IEEE binary16 round-to-nearest-even of a non-negative finite float (values in [0, 65504]).

@@ -7,6 +7,7 @@ present, every compute call raises.
 """
 from .binding import (  # noqa: F401
     QmhaError,
+    GRAN_BLOCK,
     GRAN_HEAD,
     GRAN_TENSOR,
     KERNEL_F16,

@@ -43,12 +43,13 @@ def lib() -> C.CDLL:
         L.qmha_convert_qkv_f16.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
         L.qmha_quantize_blocks.argtypes = [vp, i, i, i, i, i, vp, vp, vp]
         L.qmha_quantize_static.argtypes = [vp, C.c_int64, f, f, vp, vp]
-        L.qmha_attention_prepared.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp]
+        L.qmha_attention_prepared.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
         L.qmha_check_async_error.argtypes = []
         L.qmha_last_error.restype = C.c_char_p
         L.qmha_set_kernel.argtypes = [C.c_char_p]
         L.qmha_get_kernel.restype = C.c_char_p
         L.qmha_kernel_from_name.argtypes = [C.c_char_p]
+        L.qmha_default_granularity.argtypes = [i, i]
         L.qmha_launch_count.restype = C.c_int64
         L.qmha_version.restype = C.c_char_p
         L.qmha_shutdown.restype = None
@@ -149,8 +150,9 @@ def flash_solve(Q, K, V, d_model: int, num_heads: int, kernel: str = "fa_tc_int8
     else:
         B, N = 1, Qc.numel() // d_model
     out = torch.empty_like(Qc)
+    gran = lib().qmha_default_granularity(d_model, num_heads)   # same choice as the C solve()
     _check(lib().qmha_forward(Qc.data_ptr(), Kc.data_ptr(), Vc.data_ptr(), out.data_ptr(), B, N, d_model,
-                              num_heads, kernel_id(kernel), GRAN_HEAD, _stream_ptr()))
+                              num_heads, kernel_id(kernel), gran, _stream_ptr()))
     return out
 
 
@@ -159,7 +161,7 @@ def flash_solve_ptr(q_ptr: int, k_ptr: int, v_ptr: int, out_ptr: int, N: int, d_
     """Mirror of jax_ext.flash_solve (extensions/jax/jax_ext.cpp:12-28): raw device addresses."""
     L = lib()
     _check(L.qmha_forward(q_ptr, k_ptr, v_ptr, out_ptr, 1, N, d_model, num_heads, kernel_id(kernel),
-                          GRAN_HEAD, None))
+                          L.qmha_default_granularity(d_model, num_heads), None))
     _torch().cuda.synchronize()
     _check(L.qmha_check_async_error())
 
@@ -175,7 +177,8 @@ def forward_host(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, 
 
 
 def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None):
-    """Kernel (a).  Returns (Qp int8 [B*h,n_pad,d_pad], Kp, Vt fp16 [B*h,d_pad,n_pad], scales [3,B*h])."""
+    """Kernel (a).  Returns (Qp int8 [B*h,n_pad,d_pad], Kp, Vt fp16 [B*h,d_pad,n_pad], scales [3,B*h]
+    or, for GRAN_BLOCK, [3,B*h,n_pad/32])."""
     torch = _torch()
     _check_inputs(Q, K, V)
     Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
@@ -185,7 +188,10 @@ def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None):
     Qp = torch.empty((u, n_pad, d_pad), dtype=torch.int8, device=Q.device)
     Kp = torch.empty_like(Qp)
     Vt = torch.empty((u, d_pad, n_pad), dtype=torch.float16, device=Q.device)
-    scales = torch.empty((3, u), dtype=torch.float32, device=Q.device)
+    if gran == GRAN_BLOCK:
+        scales = torch.empty((3, u, n_pad // 32), dtype=torch.float32, device=Q.device)
+    else:
+        scales = torch.empty((3, u), dtype=torch.float32, device=Q.device)
     _check(lib().qmha_quantize_qkv(Q.data_ptr(), K.data_ptr(), V.data_ptr(), B, N, d_model, num_heads, gran,
                                    Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), scales.data_ptr(),
                                    _stream_ptr(stream)))
@@ -208,13 +214,14 @@ def convert_qkv_f16(Q, K, V, num_heads: int, stream=None):
 
 
 def attention_prepared(Qp, Kp, Vt, scales, B: int, N: int, d_model: int, num_heads: int, kernel="int8",
-                       out=None, stream=None):
-    """Kernel (b)/(c) on prepared operands; returns O [B, N, d_model] fp32."""
+                       out=None, stream=None, gran: int = GRAN_HEAD):
+    """Kernel (b)/(c) on prepared operands; returns O [B, N, d_model] fp32.  `gran` must be the
+    granularity the scales were produced with (GRAN_BLOCK: scales [3, B*h, n_pad/32])."""
     torch = _torch()
     out = torch.empty((B, N, d_model), dtype=torch.float32, device=Qp.device) if out is None else out
     _check(lib().qmha_attention_prepared(Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(),
                                          scales.data_ptr() if scales is not None else None, out.data_ptr(),
-                                         B, N, d_model, num_heads, kernel_id(kernel), _stream_ptr(stream)))
+                                         B, N, d_model, num_heads, kernel_id(kernel), gran, _stream_ptr(stream)))
     return out
 
 

@@ -42,6 +42,8 @@ struct Workspace {
   void* Vt = nullptr;
   float* scales = nullptr;
   unsigned* amax = nullptr;
+  float* aux = nullptr;    // block mode: [units][n_pad/32][2]
+  float* vmax = nullptr;   // block mode: [units]
   int* error_flag = nullptr;
   size_t qk_bytes = 0, vt_bytes = 0, scale_elems = 0;
 };
@@ -104,10 +106,12 @@ int get_workspace(int dev, size_t qk_bytes, size_t vt_bytes, size_t scale_elems,
   }
   if (scale_elems > w.scale_elems) {
     cudaDeviceSynchronize();
-    cudaFree(w.scales); cudaFree(w.amax);
-    w.scales = nullptr; w.amax = nullptr; w.scale_elems = 0;
+    cudaFree(w.scales); cudaFree(w.amax); cudaFree(w.aux); cudaFree(w.vmax);
+    w.scales = nullptr; w.amax = nullptr; w.aux = nullptr; w.vmax = nullptr; w.scale_elems = 0;
     if ((e = cudaMalloc(&w.scales, scale_elems * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc(scales)", e);
     if ((e = cudaMalloc(&w.amax, scale_elems * sizeof(unsigned))) != cudaSuccess) return fail_cuda("cudaMalloc(amax)", e);
+    if ((e = cudaMalloc(&w.aux, scale_elems * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc(aux)", e);
+    if ((e = cudaMalloc(&w.vmax, scale_elems * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc(vmax)", e);
     w.scale_elems = scale_elems;
   }
   *out = &w;
@@ -141,6 +145,10 @@ int resolve_default_kernel() {
   return g_default_kernel;
 }
 
+size_t scale_count(int units, int n_pad, int gran) {
+  return gran == QMHA_GRAN_BLOCK ? (size_t)3 * units * (n_pad / 32) : (size_t)3 * units;
+}
+
 int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, int d_model, int h,
                  int kernel, int gran, void* Qp, void* Kp, void* Vt, float* scales, unsigned* amax,
                  cudaStream_t stream) {
@@ -154,8 +162,14 @@ int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, i
   a.stream = stream;
   cudaError_t e;
   if (a.int8) {
-    if (gran != QMHA_GRAN_TENSOR && gran != QMHA_GRAN_HEAD)
-      return fail("the attention path supports QMHA_GRAN_TENSOR and QMHA_GRAN_HEAD scales");
+    if (gran == QMHA_GRAN_BLOCK) {
+      // the reference's granularity: one scale per 32-row block, single pass over the inputs
+      if ((d & 3) != 0) return fail("QMHA_GRAN_BLOCK needs a head dimension that is a multiple of 4");
+      if ((e = qmha::launch_block_quantize(a)) != cudaSuccess) return fail_cuda("block quantise launch", e);
+      g_launches += 1;
+      return 0;
+    }
+    if (gran != QMHA_GRAN_TENSOR && gran != QMHA_GRAN_HEAD) return fail("unknown scale granularity");
     // Per-(batch, head) scales: one cluster kernel reads the inputs from HBM once.  Per-tensor
     // scales need a global maximum first and keep the two-pass path (as does an odd head dim).
     static const bool two_pass_env = getenv("QMHA_TWO_PASS_QUANT") != nullptr;
@@ -182,9 +196,12 @@ int attention_variant(int kernel) {
   return QMHA_DEFAULT_ATTN_VARIANT;
 }
 
+// scales: [3][B*h] (per-head / per-tensor) or, for gran == QMHA_GRAN_BLOCK, [3][B*h][n_pad/32];
+// aux / vmax: scratch of the same element count used only in block mode.
 int attention_impl(const void* Qp, const void* Kp, const void* Vt, const float* scales, float* O,
                    int B, int N, int d_model, int h, int kernel, int* error_flag,
-                   cudaStream_t stream, long long* trace = nullptr, int variant = -1) {
+                   cudaStream_t stream, long long* trace = nullptr, int variant = -1,
+                   int gran = QMHA_GRAN_HEAD, float* aux = nullptr, float* vmax = nullptr) {
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   if (check_aligned16(O, "output")) return 1;
@@ -195,6 +212,16 @@ int attention_impl(const void* Qp, const void* Kp, const void* Vt, const float* 
   a.stream = stream;
   a.trace = trace;
   a.variant = variant >= 0 ? variant : attention_variant(kernel);
+  if (a.int8 && gran == QMHA_GRAN_BLOCK) {
+    if (!aux || !vmax) return fail("internal: block mode needs scratch");
+    const int units = B * h, nblk = n_pad / 32;
+    cudaError_t e = qmha::launch_block_aux(scales + (size_t)2 * units * nblk, aux, vmax, units, nblk, stream);
+    if (e != cudaSuccess) return fail_cuda("block aux launch", e);
+    g_launches += 1;
+    a.blk_scales = scales;
+    a.blk_aux = aux;
+    a.blk_vmax = vmax;
+  }
   std::string err;
   if (!qmha::launch_attention(a, &err)) return fail(err);
   g_launches += 1;
@@ -230,6 +257,14 @@ int qmha_set_kernel(const char* name) {
   return 0;
 }
 
+int qmha_default_granularity(int d_model, int h) {
+  const char* env = getenv("QMHA_SCALES");
+  if (env && !strcmp(env, "head")) return QMHA_GRAN_HEAD;
+  if (env && !strcmp(env, "tensor")) return QMHA_GRAN_TENSOR;
+  if (h > 0 && d_model % h == 0 && ((d_model / h) & 3) == 0) return QMHA_GRAN_BLOCK;
+  return QMHA_GRAN_HEAD;
+}
+
 const char* qmha_get_kernel(void) { return resolve_default_kernel() == QMHA_KERNEL_INT8 ? "int8" : "f16"; }
 
 int qmha_workspace_dims(int N, int d_model, int h, int* n_pad, int* d_pad) {
@@ -248,6 +283,7 @@ int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int
   if (dev < 0) return 1;
   Workspace* w;
   if (get_workspace(dev, 0, 0, (size_t)3 * B * h, &w)) return 1;
+  if (gran != QMHA_GRAN_TENSOR && gran != QMHA_GRAN_HEAD && gran != QMHA_GRAN_BLOCK) return fail("unknown scale granularity");
   if (prepare_impl(Q, K, V, B, N, d_model, h, QMHA_KERNEL_INT8, gran, Qp, Kp, Vt, scales, w->amax,
                    (cudaStream_t)stream))
     return 1;
@@ -293,14 +329,17 @@ int qmha_quantize_static(const float* X, int64_t n, float scale, float zero_poin
 }
 
 int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt, const float* scales,
-                            float* O, int B, int N, int d_model, int h, int kernel, void* stream) {
+                            float* O, int B, int N, int d_model, int h, int kernel, int gran,
+                            void* stream) {
   const int dev = require_device();
   if (dev < 0) return 1;
   if (kernel != QMHA_KERNEL_INT8 && kernel != QMHA_KERNEL_F16) return fail("unknown kernel id");
+  int d, n_pad, d_pad;
+  if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   Workspace* w;
-  if (get_workspace(dev, 0, 0, 0, &w)) return 1;
+  if (get_workspace(dev, 0, 0, scale_count(B * h, n_pad, gran), &w)) return 1;
   if (attention_impl(Qp, Kp, Vt, scales, O, B, N, d_model, h, kernel, w->error_flag,
-                     (cudaStream_t)stream))
+                     (cudaStream_t)stream, nullptr, -1, gran, w->aux, w->vmax))
     return 1;
   g_err.clear();
   return 0;
@@ -316,12 +355,14 @@ int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B
   const size_t units = (size_t)B * h;
   const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
   Workspace* w;
-  if (get_workspace(dev, units * n_pad * d_pad * elt, units * n_pad * d_pad * 2, 3 * units, &w))
+  if (get_workspace(dev, units * n_pad * d_pad * elt, units * n_pad * d_pad * 2,
+                    scale_count((int)units, n_pad, gran), &w))
     return 1;
   cudaStream_t s = (cudaStream_t)stream;
   if (prepare_impl(Q, K, V, B, N, d_model, h, kernel, gran, w->Qp, w->Kp, w->Vt, w->scales, w->amax, s))
     return 1;
-  if (attention_impl(w->Qp, w->Kp, w->Vt, w->scales, O, B, N, d_model, h, kernel, w->error_flag, s))
+  if (attention_impl(w->Qp, w->Kp, w->Vt, w->scales, O, B, N, d_model, h, kernel, w->error_flag, s,
+                     nullptr, -1, gran, w->aux, w->vmax))
     return 1;
   g_err.clear();
   return 0;
@@ -369,7 +410,9 @@ void solve(const float* Q, const float* K, const float* V, float* output, int N,
   // Synchronous on return like the reference (launchers.h:64); errors are recorded, reported on
   // stderr and queryable with qmha_last_error() — solve() itself stays void.
   const int kernel = resolve_default_kernel();
-  int rc = qmha_forward(Q, K, V, output, 1, N, d_model, h, kernel, QMHA_GRAN_HEAD, nullptr);
+  // Scales at the reference's own granularity (one per 32-row tile, fa_tc_int8_b.cu:484-518) when the
+  // head dimension allows the vectorised single-pass quantiser, per (batch, head) otherwise.
+  int rc = qmha_forward(Q, K, V, output, 1, N, d_model, h, kernel, qmha_default_granularity(d_model, h), nullptr);
   if (rc == 0) {
     cudaError_t e = cudaStreamSynchronize(nullptr);
     if (e != cudaSuccess) rc = fail_cuda("solve", e);
@@ -417,7 +460,8 @@ int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, 
   const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
   const size_t qk1 = units1 * n_pad * d_pad * elt, vt1 = units1 * n_pad * d_pad * 2;
   Workspace* w;
-  if (get_workspace(dev, 2 * qk1, 2 * vt1, 2 * 3 * units1, &w)) return 1;
+  const size_t sc1 = scale_count((int)units1, n_pad, gran);
+  if (get_workspace(dev, 2 * qk1, 2 * vt1, 2 * sc1, &w)) return 1;
   for (int b = 0; b < B; ++b) {
     Slot& sl = (*slots)[b & 1];
     const size_t off = (size_t)b * slab;
@@ -430,10 +474,12 @@ int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, 
     void* Qp = (char*)w->Qp + half * qk1;
     void* Kp = (char*)w->Kp + half * qk1;
     void* Vt = (char*)w->Vt + half * vt1;
-    float* sc = w->scales + half * 3 * units1;
-    unsigned* am = w->amax + half * 3 * units1;
+    float* sc = w->scales + half * sc1;
+    unsigned* am = w->amax + half * sc1;
     if (prepare_impl(sl.q, sl.k, sl.v, 1, N, d_model, h, kernel, gran, Qp, Kp, Vt, sc, am, sl.s)) return 1;
-    if (attention_impl(Qp, Kp, Vt, sc, sl.o, 1, N, d_model, h, kernel, w->error_flag, sl.s)) return 1;
+    if (attention_impl(Qp, Kp, Vt, sc, sl.o, 1, N, d_model, h, kernel, w->error_flag, sl.s, nullptr, -1,
+                       gran, w->aux + half * sc1, w->vmax + half * sc1))
+      return 1;
     if ((e = cudaMemcpyAsync(O + off, sl.o, slab * 4, cudaMemcpyDeviceToHost, sl.s)) != cudaSuccess)
       return fail_cuda("D2H copy", e);
   }
@@ -451,7 +497,7 @@ void qmha_shutdown(void) {
   for (auto& kv : g_ws) {
     cudaSetDevice(kv.first);
     Workspace& w = kv.second;
-    cudaFree(w.Qp); cudaFree(w.Kp); cudaFree(w.Vt); cudaFree(w.scales); cudaFree(w.amax);
+    cudaFree(w.Qp); cudaFree(w.Kp); cudaFree(w.Vt); cudaFree(w.scales); cudaFree(w.amax); cudaFree(w.aux); cudaFree(w.vmax);
     cudaFree(w.error_flag);
   }
   g_ws.clear();

@@ -242,7 +242,66 @@ __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t 
   }
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kTrace>
+// ---- per-32-key-block scale mode (the reference's granularity, INT8 only) -----------------------
+// A 64-key half-step spans two K/V blocks: columns [0,32) use (c0, b0), columns [32,64) (c1, b1)
+// where c_g = sQ(row block)·sK(block g)·log2e/sqrt(d) and b_g = -(2^23·1.5·c_g + m) + log2 r_g folds the
+// V block scale ratio r_g = sV_g / sV_max into the exponent; the un-scaled row sum is recovered per
+// block as (sum of P')/r_g.  All of it is compile-time column selection: no per-element cost.
+struct StepConsts {
+  float c0, c1, lr0, lr1, ir0, ir1;
+};
+
+template <bool kMasked>
+__device__ __forceinline__ float tile_row_max_blk(uint32_t (&s)[kHN], float c0, float c1, int n_valid) {
+  if constexpr (kMasked) {
+#pragma unroll
+    for (int i = 0; i < kHN; ++i)
+      if (i >= n_valid) s[i] = (uint32_t)(-(1 << 22));
+  }
+  int lo0 = max((int)s[0], (int)s[1]), lo1 = max((int)s[2], (int)s[3]);
+  int hi0 = max((int)s[32], (int)s[33]), hi1 = max((int)s[34], (int)s[35]);
+#pragma unroll
+  for (int i = 4; i < 32; i += 4) {
+    lo0 = max(max(lo0, (int)s[i + 0]), (int)s[i + 1]);
+    lo1 = max(max(lo1, (int)s[i + 2]), (int)s[i + 3]);
+    hi0 = max(max(hi0, (int)s[32 + i + 0]), (int)s[32 + i + 1]);
+    hi1 = max(max(hi1, (int)s[32 + i + 2]), (int)s[32 + i + 3]);
+  }
+  return fmaxf((float)max(lo0, lo1) * c0, (float)max(hi0, hi1) * c1);
+}
+
+template <bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2>
+__device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint32_t (&p)[kHN / 2],
+                                                 const StepConsts& k, float m_used, int n_valid,
+                                                 uint64_t (&ls)[2]) {
+  const float b0 = k.lr0 - fmaf(kMagicF, k.c0, m_used);
+  const float b1 = k.lr1 - fmaf(kMagicF, k.c1, m_used);
+  const uint64_t c2[2] = {pack2(k.c0, k.c0), pack2(k.c1, k.c1)};
+  const uint64_t bias2[2] = {pack2(b0, b0), pack2(b1, b1)};
+#pragma unroll
+  for (int i = kBegin; i < kEnd; ++i) {
+    constexpr int kHalf = kHN / 4;  // pairs per 32-key block
+    const int g = i >= kHalf ? 1 : 0;
+    const float f0 = __int_as_float((int)s[2 * i] + kMagicI2F);
+    const float f1 = __int_as_float((int)s[2 * i + 1] + kMagicI2F);
+    float x0, x1, e0, e1;
+    unpack2(ffma2(pack2(f0, f1), c2[g], bias2[g]), x0, x1);
+    if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery > 0 ? kPolyEvery : 1) - 1) {
+      exp2_poly_pair(x0, x1, e0, e1);
+    } else {
+      e0 = ex2_approx(x0);
+      e1 = ex2_approx(x1);
+    }
+    if constexpr (kMasked) {
+      if (2 * i >= n_valid) e0 = 0.f;
+      if (2 * i + 1 >= n_valid) e1 = 0.f;
+    }
+    ls[g] = fadd2(ls[g], pack2(e0, e1));
+    p[i] = pack_f16x2(e0, e1);
+  }
+}
+
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, AttnParams prm) {
@@ -433,9 +492,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tS = tmem_base + lane_addr + (t ? kColS1 : kColS0);
     const uint32_t tO = tmem_base + lane_addr + (t ? kColO1 : kColO0);
 
+    static_assert(!kBlk || kInt8, "block scales only exist for the INT8 variant");
     float c = prm.scale_log2;  // log2(e) / sqrt(d)
     float out_scale = 1.0f;
-    if constexpr (kInt8) {
+    const int nblk = prm.n_pad / 32;
+    if constexpr (kBlk) {
+      // c = log2e/sqrt(d) * sQ of this row's 32-row block; the K/V block factors come per step
+      const int qblk = (q_base + t * kBM + row_in_tile) >> 5;
+      c *= __ldg(prm.blk_scales + (size_t)unit * nblk + qblk);
+      out_scale = __ldg(prm.blk_vmax + unit);
+    } else if constexpr (kInt8) {
       const float sq = prm.scales[unit];
       const float sk = prm.scales[prm.units + unit];
       out_scale = prm.scales[2 * prm.units + unit];
@@ -443,7 +509,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 
     float m_used = -INFINITY;
-    uint64_t lsum[2] = {0ull, 0ull};  // four fp32 partial row sums (packed pairs)
+    uint64_t lsum[2] = {0ull, 0ull};  // four fp32 partial row sums (packed pairs); block mode: l_acc
+    float l_acc = 0.f;
     const int n_half = prm.n_half_steps;
     const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0;
     long long* tr = kTrace ? prm.trace + (size_t)t * n_half * 4 : nullptr;
@@ -452,6 +519,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // run, the scores of step i+1 (already computed by the tensor core: S is double-buffered)
     // are fetched from TMEM and their row max is taken, so tcgen05.ld latency and the max
     // dependency chain hide under the MUFU work.  Two register arrays (sA, sB) alternate.
+
+    // block mode: scale factors of the two 32-key blocks of half-step i (broadcast loads)
+    auto load_consts = [&](int i) {
+      StepConsts k{c, c, 0.f, 0.f, 1.f, 1.f};
+      if constexpr (kBlk) {
+        const float* sk = prm.blk_scales + ((size_t)prm.units + unit) * nblk + 2 * i;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(prm.blk_aux + ((size_t)unit * nblk + 2 * i) * 2));
+        k.c0 = c * __ldg(sk);
+        k.c1 = c * __ldg(sk + 1);
+        k.lr0 = a.x; k.ir0 = a.y; k.lr1 = a.z; k.ir1 = a.w;
+      }
+      return k;
+    };
+    auto row_max = [&](uint32_t (&sx)[kHN], const StepConsts& k, bool masked, int n_valid) {
+      if constexpr (kBlk) {
+        return masked ? tile_row_max_blk<true>(sx, k.c0, k.c1, n_valid) : tile_row_max_blk<false>(sx, k.c0, k.c1, kHN);
+      } else {
+        return masked ? tile_row_max<kInt8, true>(sx, c, n_valid) : tile_row_max<kInt8, false>(sx, c, kHN);
+      }
+    };
+    // block mode: add this step's per-block sums of P' = p*r back as p
+    auto fold_sums = [&](const uint64_t (&ls)[2], const StepConsts& k) {
+      float a0, a1, b0, b1;
+      unpack2(ls[0], a0, a1);
+      unpack2(ls[1], b0, b1);
+      l_acc = fmaf(a0 + a1, k.ir0, fmaf(b0 + b1, k.ir1, l_acc));
+    };
 
     // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld)
     auto fetch = [&](int i, uint32_t (&dst)[kHN]) {
@@ -474,6 +568,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint64_t alpha2 = pack2(alpha, alpha);
           lsum[0] = fmul2(lsum[0], alpha2);
           lsum[1] = fmul2(lsum[1], alpha2);
+          l_acc *= alpha;
           mbar_wait(&bars->pv_done[t], (i - 1) & 1, err_flag, 311 + t, dead);
           dead = __any_sync(0xffffffffu, dead);
           tc_fence_after();
@@ -501,64 +596,86 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (tracer) tr[i * 4 + 3] = clock64();
     };
     // pipelined step: exp of `cur` (step i, unmasked) overlapped with fetch + max of step i+1.
-    auto pipe_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur, uint32_t (&nxt)[kHN], float& mt_nxt) {
+    auto pipe_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur, const StepConsts& kc,
+                         uint32_t (&nxt)[kHN], float& mt_nxt, StepConsts& kn) {
       if (tracer) tr[i * 4 + 0] = clock64();
       update_max(i, mt_cur);
       uint32_t p[kHN / 2];
+      uint64_t ls[2] = {0ull, 0ull};
       // S_t(i+1) is issued behind P·V of step i-1, i.e. it lands roughly a third of the way into
       // this step: run part of the exponentials first so the fetch does not stall on it.
-      tile_row_exp<kInt8, false, kPolyEvery, 0, 12>(cur, p, c, m_used, kHN, lsum);
+      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, 0, 12>(cur, p, kc, m_used, kHN, ls);
+      else tile_row_exp<kInt8, false, kPolyEvery, 0, 12>(cur, p, c, m_used, kHN, lsum);
       fetch(i + 1, nxt);
-      tile_row_exp<kInt8, false, kPolyEvery, 12, 22>(cur, p, c, m_used, kHN, lsum);
+      kn = load_consts(i + 1);
+      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, 12, 22>(cur, p, kc, m_used, kHN, ls);
+      else tile_row_exp<kInt8, false, kPolyEvery, 12, 22>(cur, p, c, m_used, kHN, lsum);
       tmem_wait_ld();
-      mt_nxt = tile_row_max<kInt8, false>(nxt, c, kHN);
-      tile_row_exp<kInt8, false, kPolyEvery, 22, kHN / 2>(cur, p, c, m_used, kHN, lsum);
+      mt_nxt = row_max(nxt, kn, false, kHN);
+      if constexpr (kBlk) {
+        tile_row_exp_blk<false, kPolyEvery, 22, kHN / 2>(cur, p, kc, m_used, kHN, ls);
+        fold_sums(ls, kc);
+      } else {
+        tile_row_exp<kInt8, false, kPolyEvery, 22, kHN / 2>(cur, p, c, m_used, kHN, lsum);
+      }
       if (tracer) tr[i * 4 + 2] = clock64();
       publish(i, p);
     };
     // step whose scores are already in registers, nothing left to prefetch (unmasked).
-    auto drain_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur) {
+    auto drain_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur, const StepConsts& kc) {
       if (tracer) tr[i * 4 + 0] = clock64();
       update_max(i, mt_cur);
       uint32_t p[kHN / 2];
-      tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum);
+      if constexpr (kBlk) {
+        uint64_t ls[2] = {0ull, 0ull};
+        tile_row_exp_blk<false, kPolyEvery>(cur, p, kc, m_used, kHN, ls);
+        fold_sums(ls, kc);
+      } else {
+        tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum);
+      }
       if (tracer) tr[i * 4 + 2] = clock64();
       publish(i, p);
     };
 
     uint32_t sA[kHN], sB[kHN];
     float mtA = 0.f, mtB = 0.f;
+    StepConsts kA = load_consts(0), kB = kA;
     int i = 0;
     if (n_half >= 2) {
       // steps 0 .. n_half-2 are full (unmasked) by construction; only the last one can be ragged
       fetch(0, sA);
       tmem_wait_ld();
-      mtA = tile_row_max<kInt8, false>(sA, c, kHN);
+      mtA = row_max(sA, kA, false, kHN);
       bool in_a = true;
       while (i + 2 < n_half) {
-        pipe_step(i, sA, mtA, sB, mtB);
+        pipe_step(i, sA, mtA, kA, sB, mtB, kB);
         ++i;
         if (!(i + 2 < n_half)) { in_a = false; break; }
-        pipe_step(i, sB, mtB, sA, mtA);
+        pipe_step(i, sB, mtB, kB, sA, mtA, kA);
         ++i;
       }
-      if (in_a) drain_step(i, sA, mtA);
-      else drain_step(i, sB, mtB);
+      if (in_a) drain_step(i, sA, mtA, kA);
+      else drain_step(i, sB, mtB, kB);
       ++i;
     }
     {
       // last step (i == n_half-1): may cover fewer than 64 existing keys
       if (tracer) tr[i * 4 + 0] = clock64();
       fetch(i, sA);
+      const StepConsts kl = load_consts(i);
       tmem_wait_ld();
       const int n_valid = prm.N - i * kHN;  // >= 1
+      const bool masked = n_valid < kHN;
       uint32_t p[kHN / 2];
-      if (n_valid < kHN) {
-        update_max(i, tile_row_max<kInt8, true>(sA, c, n_valid));
-        tile_row_exp<kInt8, true, kPolyEvery>(sA, p, c, m_used, n_valid, lsum);
+      update_max(i, row_max(sA, kl, masked, n_valid));
+      if constexpr (kBlk) {
+        uint64_t ls[2] = {0ull, 0ull};
+        if (masked) tile_row_exp_blk<true, kPolyEvery>(sA, p, kl, m_used, n_valid, ls);
+        else tile_row_exp_blk<false, kPolyEvery>(sA, p, kl, m_used, kHN, ls);
+        fold_sums(ls, kl);
       } else {
-        update_max(i, tile_row_max<kInt8, false>(sA, c, kHN));
-        tile_row_exp<kInt8, false, kPolyEvery>(sA, p, c, m_used, kHN, lsum);
+        if (masked) tile_row_exp<kInt8, true, kPolyEvery>(sA, p, c, m_used, n_valid, lsum);
+        else tile_row_exp<kInt8, false, kPolyEvery>(sA, p, c, m_used, kHN, lsum);
       }
       if (tracer) tr[i * 4 + 2] = clock64();
       publish(i, p);
@@ -572,7 +689,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float l, la, lb, lc, ld;
     unpack2(lsum[0], la, lb);
     unpack2(lsum[1], lc, ld);
-    l = (la + lb) + (lc + ld);
+    l = kBlk ? l_acc : (la + lb) + (lc + ld);
     const float inv = (l > 0.f) ? out_scale / l : 0.f;  // fa_tc_int8_b.cu:549-553 guard
     const int row = q_base + t * kBM + row_in_tile;
     const int b = unit / prm.H, head = unit % prm.H;
@@ -659,7 +776,7 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
   return true;
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kTrace>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD>;
   const uint64_t units = (uint64_t)a.B * a.H;
@@ -668,7 +785,7 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
       !make_map_2d(&tk, a.Kp, C::kEltQK, units * a.n_pad, kD, kBN, C::kAtomQK / C::kEltQK, err) ||
       !make_map_2d(&tv, a.Vt, 2, units * kD, a.n_pad, kD, 64, err))
     return false;
-  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kTrace>;
+  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace>;
   {  // per device (context) attribute; cheap enough to set on every launch
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
@@ -679,6 +796,9 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.scales = a.scales;
   p.error_flag = a.error_flag;
   p.trace = a.trace;
+  p.blk_scales = a.blk_scales;
+  p.blk_aux = a.blk_aux;
+  p.blk_vmax = a.blk_vmax;
   p.B = a.B; p.N = a.N; p.H = a.H; p.d = a.d;
   p.n_pad = a.n_pad;
   p.units = (int)units;
@@ -698,27 +818,35 @@ bool launch_attention(const AttnLaunch& a, std::string* err) {
   if (a.units_y_limit_exceeded()) { *err = "B*h exceeds the CUDA grid.y limit (65535)"; return false; }
   // a.variant = k: exp2 of every k-th score pair goes to the FMA-pipe polynomial (0 = all MUFU)
   const int poly = a.variant;
+  const bool blk = a.blk_scales != nullptr;
+  if (blk && !a.int8) { *err = "block scales require the INT8 variant"; return false; }
   if (a.trace) {
     if (!(a.int8 && a.d_pad == 128)) { *err = "tracing is only built for the INT8 d=128 kernel"; return false; }
-    return launch_cfg<true, 128, 0, true>(a, err);
+    return blk ? launch_cfg<true, 128, 0, true, true>(a, err) : launch_cfg<true, 128, 0, false, true>(a, err);
   }
-#define QMHA_DISPATCH(INT8, D)                                   \
-  switch (poly) {                                                \
-    case 0: return launch_cfg<INT8, D, 0, false>(a, err);        \
-    case 4: return launch_cfg<INT8, D, 4, false>(a, err);        \
-    case 8: return launch_cfg<INT8, D, 8, false>(a, err);        \
+#define QMHA_DISPATCH(INT8, BLK, D)                                   \
+  switch (poly) {                                                     \
+    case 0: return launch_cfg<INT8, D, 0, BLK, false>(a, err);        \
+    case 4: return launch_cfg<INT8, D, 4, BLK, false>(a, err);        \
+    case 8: return launch_cfg<INT8, D, 8, BLK, false>(a, err);        \
   }
-  if (a.int8) {
+  if (a.int8 && blk) {
     switch (a.d_pad) {
-      case 32: QMHA_DISPATCH(true, 32) break;
-      case 64: QMHA_DISPATCH(true, 64) break;
-      case 128: QMHA_DISPATCH(true, 128) break;
+      case 32: QMHA_DISPATCH(true, true, 32) break;
+      case 64: QMHA_DISPATCH(true, true, 64) break;
+      case 128: QMHA_DISPATCH(true, true, 128) break;
+    }
+  } else if (a.int8) {
+    switch (a.d_pad) {
+      case 32: QMHA_DISPATCH(true, false, 32) break;
+      case 64: QMHA_DISPATCH(true, false, 64) break;
+      case 128: QMHA_DISPATCH(true, false, 128) break;
     }
   } else {
     switch (a.d_pad) {
-      case 32: QMHA_DISPATCH(false, 32) break;
-      case 64: QMHA_DISPATCH(false, 64) break;
-      case 128: QMHA_DISPATCH(false, 128) break;
+      case 32: QMHA_DISPATCH(false, false, 32) break;
+      case 64: QMHA_DISPATCH(false, false, 64) break;
+      case 128: QMHA_DISPATCH(false, false, 128) break;
     }
   }
 #undef QMHA_DISPATCH

@@ -10,6 +10,9 @@ struct AttnParams {
   float* O;             // [B, N, H*d] fp32
   const float* scales;  // [3, units] (INT8 variant) or nullptr
   int* error_flag;      // device int: 0 = ok, otherwise the wait site that timed out
+  const float* blk_scales;  // block mode: [3][units][n_pad/32] raw scales (Q, K, V), else nullptr
+  const float* blk_aux;     // block mode: [units][n_pad/32][2] = {log2 r, 1/r}, r = sV_block/sV_max
+  const float* blk_vmax;    // block mode: [units] largest V block scale
   long long* trace;     // debug timeline buffer [3 roles][n_half_steps][4] (traced build only)
   int B, N, H, d;
   int n_pad;            // padded sequence length of the prepared operands (multiple of 256)
@@ -26,6 +29,9 @@ struct AttnLaunch {
   const float* scales;
   float* O;
   int* error_flag;
+  const float* blk_scales = nullptr;  // non-null selects the per-32-row-block scale kernel (INT8)
+  const float* blk_aux = nullptr;
+  const float* blk_vmax = nullptr;
   long long* trace = nullptr;  // device buffer; non-null selects the traced instantiation
   int variant = 0;             // k > 0: exp2 of every k-th score pair on the FMA-pipe polynomial
   int B, N, H, d, n_pad, d_pad;

@@ -195,6 +195,134 @@ prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
 }
 
 // ------------------------------------------------------------------------------------------------
+// block_quantize_kernel: the reference's own granularity — one scale per (batch, head, 32-row
+// block), exactly fp32_to_int8sram on a Br x d / Bc x d tile (fa_tc_int8_b.cu:484,496,518) — in
+// ONE pass: a CTA keeps its 128-row tile (4 blocks) in registers, reduces the four block maxima,
+// then quantises from registers.  HBM traffic = algorithmic (read fp32 once, write codes once).
+//   grid = (n_pad/128, B*H, 3);  scales[z][unit][n_pad/32]
+template <int kD>
+__global__ void __launch_bounds__(kPrepThreads)
+block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                      const float* __restrict__ V, float* __restrict__ scales,
+                      int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
+                      int N, int H, int d, int n_pad) {
+  const int z = blockIdx.z, unit = blockIdx.y;
+  const int b = unit / H, head = unit % H;
+  const int n0 = blockIdx.x * kPrepRows;
+  const float* X = z == 0 ? Q : (z == 1 ? K : V);
+  const int d_model = H * d;
+  const float* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+
+  constexpr int kVecPerRow = kD / 4;
+  constexpr int kRowsPerIter = kPrepThreads / kVecPerRow;  // 8 / 16 / 32 rows per pass
+  constexpr int kLoads = kPrepRows / kRowsPerIter;          // 16 / 8 / 4 float4 per thread
+  constexpr int kPerBlock = 32 / kRowsPerIter;              // loads of one thread per 32-row block
+  const int vec = threadIdx.x % kVecPerRow;
+  const int rsub = threadIdx.x / kVecPerRow;
+  const bool col_ok = vec * 4 < d;                          // host guarantees d % 4 == 0
+
+  float4 x[kLoads];
+#pragma unroll
+  for (int k = 0; k < kLoads; ++k) {
+    const int n = n0 + rsub + k * kRowsPerIter;
+    x[k] = (n < N && col_ok) ? ldg_f4(src + (size_t)n * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // block maxima: thread -> warp (shuffle) -> CTA (shared memory)
+  __shared__ float s_max[kPrepThreads / 32][4];
+  float m[4];
+#pragma unroll
+  for (int blk = 0; blk < 4; ++blk) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < kPerBlock; ++k) v = absmax4(v, x[blk * kPerBlock + k]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    m[blk] = v;
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) s_max[threadIdx.x >> 5][blk] = m[blk];
+  }
+  __syncthreads();
+  float inv_sc[4];
+#pragma unroll
+  for (int blk = 0; blk < 4; ++blk) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPrepThreads / 32; ++w) v = fmaxf(v, s_max[w][blk]);
+    const float sc = fmaxf(v / 127.0f, 1e-8f);  // fa_tc_int8_b.cu:104
+    inv_sc[blk] = 1.0f / sc;                    // fa_tc_int8_b.cu:106
+    if (threadIdx.x == 0)
+      scales[((size_t)z * gridDim.y + unit) * (n_pad / 32) + (n0 / 32) + blk] = sc;
+  }
+
+  if (z < 2) {
+    int8_t* dst = z == 0 ? Qp : Kp;
+#pragma unroll
+    for (int k = 0; k < kLoads; ++k) {
+      const int n = n0 + rsub + k * kRowsPerIter;
+      const float inv = inv_sc[k / kPerBlock];
+      const int q0 = quant1(x[k].x, inv), q1 = quant1(x[k].y, inv);
+      const int q2 = quant1(x[k].z, inv), q3 = quant1(x[k].w, inv);
+      const uint32_t pk = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) |
+                          ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+      *reinterpret_cast<uint32_t*>(dst + ((size_t)unit * n_pad + n) * kD + vec * 4) = pk;
+    }
+  } else {
+    constexpr int kStride = kD + 2;
+    __shared__ __half tile[kPrepRows * kStride];
+#pragma unroll
+    for (int k = 0; k < kLoads; ++k) {
+      const int r = rsub + k * kRowsPerIter;
+      const float inv = inv_sc[k / kPerBlock];
+      tile[r * kStride + vec * 4 + 0] = __float2half_rn((float)quant1(x[k].x, inv));
+      tile[r * kStride + vec * 4 + 1] = __float2half_rn((float)quant1(x[k].y, inv));
+      tile[r * kStride + vec * 4 + 2] = __float2half_rn((float)quant1(x[k].z, inv));
+      tile[r * kStride + vec * 4 + 3] = __float2half_rn((float)quant1(x[k].w, inv));
+    }
+    __syncthreads();
+    const int kp = threadIdx.x & 63;
+    for (int dd = threadIdx.x >> 6; dd < kD; dd += kPrepThreads / 64) {
+      __half2 o2 = __halves2half2(tile[(2 * kp) * kStride + dd], tile[(2 * kp + 1) * kStride + dd]);
+      *reinterpret_cast<__half2*>(Vt + ((size_t)unit * kD + dd) * n_pad + n0 + 2 * kp) = o2;
+    }
+  }
+}
+
+template <int kD>
+cudaError_t launch_block_cfg(const PrepareArgs& a) {
+  dim3 grid(a.n_pad / kPrepRows, a.B * a.H, 3);
+  block_quantize_kernel<kD><<<grid, kPrepThreads, 0, a.stream>>>(
+      a.Q, a.K, a.V, a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
+      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad);
+  return cudaGetLastError();
+}
+
+// V-side helper of the attention kernel in block mode: per unit the largest V scale and, per
+// 32-key block, log2(r) and 1/r with r = sV_block / sV_max (see attn_fwd.cu).
+//   aux[unit][nblk][2];  vmax[unit]
+__global__ void block_aux_kernel(const float* __restrict__ scales_v, float* __restrict__ aux,
+                                 float* __restrict__ vmax, int nblk) {
+  const int unit = blockIdx.x;
+  const float* sv = scales_v + (size_t)unit * nblk;
+  __shared__ float s_red[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) m = fmaxf(m, sv[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
+  if (threadIdx.x == 0) vmax[unit] = m;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    const float r = sv[i] / m;
+    aux[((size_t)unit * nblk + i) * 2 + 0] = log2f(r);
+    aux[((size_t)unit * nblk + i) * 2 + 1] = 1.0f / r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Reference-granularity quantiser in the input layout: one warp per (batch, head, row block).
 __global__ void quantize_blocks_kernel(const float* __restrict__ X, int8_t* __restrict__ q,
                                        float* __restrict__ scales, int B, int N, int H, int d,
@@ -416,6 +544,22 @@ cudaError_t launch_fused_quantize(const PrepareArgs& a) {
     case 128: return launch_fused_cfg<128>(a);
   }
   return cudaErrorInvalidValue;
+}
+
+// Single-pass INT8 preparation with per-(batch, head, 32-row block) scales (requires d % 4 == 0).
+cudaError_t launch_block_quantize(const PrepareArgs& a) {
+  switch (a.d_pad) {
+    case 32: return launch_block_cfg<32>(a);
+    case 64: return launch_block_cfg<64>(a);
+    case 128: return launch_block_cfg<128>(a);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_block_aux(const float* scales_v, float* aux, float* vmax, int units, int nblk,
+                             cudaStream_t stream) {
+  block_aux_kernel<<<units, 256, 0, stream>>>(scales_v, aux, vmax, nblk);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_prepare(const PrepareArgs& a) {

@@ -22,6 +22,11 @@ struct PrepareArgs {
 cudaError_t launch_absmax_and_scales(const PrepareArgs& a, unsigned* amax_bits, int per_tensor);
 // absmax + quantise + re-layout in ONE launch (cluster kernel; INT8, per-(batch,head) scales, d%4==0).
 cudaError_t launch_fused_quantize(const PrepareArgs& a);
+// single-pass quantise with the reference's per-32-row-block scales; scales = [3][B*H][n_pad/32]
+cudaError_t launch_block_quantize(const PrepareArgs& a);
+// per unit max V scale + per block {log2 r, 1/r}, r = sV_block / sV_max (attention, block mode)
+cudaError_t launch_block_aux(const float* scales_v, float* aux, float* vmax, int units, int nblk,
+                             cudaStream_t stream);
 // quantise / convert + re-layout (1 launch).
 cudaError_t launch_prepare(const PrepareArgs& a);
 cudaError_t launch_quantize_blocks(const float* X, int B, int N, int H, int d, int block_rows,

@@ -289,3 +289,52 @@ def test_headline_shape_sampled_rows_vs_oracle(qm, torch, oracle):
 
 def test_native_library_was_really_used(qm):
     assert qm.launch_count() > 0
+
+
+# ---------------------------------------------------------------------------------- block scales
+@pytest.mark.parametrize("shape", [(1, 128, 128, 1), (2, 300, 256, 2), (1, 1024, 256, 2), (1, 50, 64, 8), (1, 2048, 512, 4)])
+def test_block_scale_mode_reference_granularity(qm, torch, oracle, shape):
+    """QMHA_GRAN_BLOCK = the reference's own granularity (one scale per 32-row tile per head,
+    fa_tc_int8_b.cu:484,496,518).  Codes and scales bit-exact vs the CPU restatement; attention
+    tight against the emulated-INT8 model on the same tensors; rel-L2 vs FP32 <= 1e-2 even on the
+    golden (normal) inputs, where coarser scales sit at ~1e-2."""
+    B, N, dm, h = shape
+    d = dm // h
+    q, k, v = (np.stack([a] * B) for a in oracle.golden_inputs(N, dm, h))
+    if B > 1:
+        q[1] *= 1.5
+        v[1] *= 0.25
+    tq, tk, tv = _dev(torch, q, k, v)
+    Qp, Kp, Vt, sc = qm.quantize_qkv(tq, tk, tv, h, qm.GRAN_BLOCK)
+    nb = -(-N // 32)
+    emu_in = []
+    for i, (x, packed, unpack) in enumerate(((q, Qp, _unpack_rows), (k, Kp, _unpack_rows), (v, Vt, _unpack_vt))):
+        codes, s = oracle.quantize(x, h, "block", 32)
+        assert np.array_equal(unpack(packed, B, N, h, d), codes.astype(np.float32) if i == 2 else codes)
+        assert np.array_equal(sc[i].cpu().numpy()[:, :nb].reshape(-1), s)
+        emu_in.append((codes, s))
+    out = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_BLOCK)
+    torch.cuda.synchronize()
+    qm.binding.check_async_error()
+    o = out.cpu().numpy()
+    emu = oracle.mha_int8_emulated_block(emu_in[0][0], emu_in[1][0], emu_in[2][0], emu_in[0][1], emu_in[1][1],
+                                         emu_in[2][1], h, 32, "f16")
+    assert _err(o, emu)[1] <= KERNEL_VS_EMU_REL_L2
+    mx, rel = _err(o, oracle.mha(q, k, v, h, "f64"))
+    assert mx <= INT8_MAX_ABS and rel <= INT8_REL_L2, (mx, rel)
+
+
+def test_solve_uses_block_scales_by_default(qm, torch, oracle):
+    q, k, v = oracle.golden_inputs(512, 256, 2)
+    tq, tk, tv = _dev(torch, q, k, v)
+    assert qm.lib().qmha_default_granularity(256, 2) == qm.GRAN_BLOCK
+    assert qm.lib().qmha_default_granularity(30, 2) == qm.GRAN_HEAD   # d = 15: scalar two-pass path
+    out = qm.solve(tq, tk, tv, 512, 256, 2)
+    blk = qm.forward(tq, tk, tv, 2, kernel="int8", gran=qm.GRAN_BLOCK)
+    torch.cuda.synchronize()
+    assert torch.equal(out, blk)
+    # odd head dimension still works (per-head scales, scalar loads)
+    q, k, v = oracle.golden_inputs(96, 30, 2)
+    tq, tk, tv = _dev(torch, q, k, v)
+    out = qm.solve(tq, tk, tv, 96, 30, 2)
+    assert _err(out.cpu().numpy(), oracle.mha(q, k, v, 2, "f64"))[0] <= INT8_MAX_ABS
