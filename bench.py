@@ -290,6 +290,12 @@ def run_native(args):
     # int8: Q,K int8 (1 B) + V codes as fp16 (2 B) = 4E out; f16: 6E out.  3*E*4 in.
     prep_bytes = 3 * E * 4 + (4 * E if kernel == "int8" else 6 * E)
     pk = peaks()
+    traffic = None
+    try:   # per-launch DRAM traffic measured once with `ncu --set full` (profiles/r01/traffic.json)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
+        traffic = tj["attn_fwd_kernel"].get(f"{args.workload}:{kernel}")
+    except (OSError, KeyError, ValueError):
+        pass
     value = flops_all / (ms_step / 1e3) / 1e12
     attn_tflops = flops_rank / (attn_ms / 1e3) / 1e12
     line = {
@@ -303,7 +309,8 @@ def run_native(args):
         "attn_ms": attn_ms, "attn_tflops_per_gpu": attn_tflops, "prep_ms": prep_ms,
         "prep_gbs_algorithmic": prep_bytes / (prep_ms / 1e3) / 1e9, "prep_frac_of_hbm": prep_bytes / (prep_ms / 1e3) / 1e9 / pk["hbm"],
         "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel", "achieved": attn_tflops, "peak": pk["bf16_sustained"],
-                     "unit": "TFLOP/s", "frac": attn_tflops / pk["bf16_sustained"], "traffic": None,
+                     "unit": "TFLOP/s", "frac": attn_tflops / pk["bf16_sustained"], "traffic": traffic,
+                     "traffic_unit": "bytes of DRAM read+write per launch (ncu); algorithmic operand+output bytes = %d" % (E * (1 + 1 + 2) + E * 4) if kernel == "int8" else "bytes",
                      "peak_src": f"{pk['src']} dense bf16 cuBLAS GEMM, sustained (kernel timed inside the step loop)",
                      "frac_of_nominal_int8_4500": attn_tflops / 4500.0,
                      "frac_of_nominal_mixed_3000": attn_tflops / 3000.0},
