@@ -301,7 +301,7 @@ __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint3
   }
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 20, int kFb = 28>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, AttnParams prm) {
@@ -602,21 +602,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       update_max(i, mt_cur);
       uint32_t p[kHN / 2];
       uint64_t ls[2] = {0ull, 0ull};
-      // S_t(i+1) is issued behind P·V of step i-1, i.e. it lands roughly a third of the way into
-      // this step: run part of the exponentials first so the fetch does not stall on it.
-      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, 0, 12>(cur, p, kc, m_used, kHN, ls);
-      else tile_row_exp<kInt8, false, kPolyEvery, 0, 12>(cur, p, c, m_used, kHN, lsum);
+      // S_t(i+1) is issued behind P·V of step i-1, i.e. it lands roughly half way into this step:
+      // run kFa of the 32 exponential pairs first so the fetch does not stall on it, take the row
+      // max of the fetched scores after kFb pairs (measured best of several placements: 20 / 28).
+      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, 0, kFa>(cur, p, kc, m_used, kHN, ls);
+      else tile_row_exp<kInt8, false, kPolyEvery, 0, kFa>(cur, p, c, m_used, kHN, lsum);
       fetch(i + 1, nxt);
       kn = load_consts(i + 1);
-      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, 12, 22>(cur, p, kc, m_used, kHN, ls);
-      else tile_row_exp<kInt8, false, kPolyEvery, 12, 22>(cur, p, c, m_used, kHN, lsum);
+      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, kFa, kFb>(cur, p, kc, m_used, kHN, ls);
+      else tile_row_exp<kInt8, false, kPolyEvery, kFa, kFb>(cur, p, c, m_used, kHN, lsum);
       tmem_wait_ld();
       mt_nxt = row_max(nxt, kn, false, kHN);
       if constexpr (kBlk) {
-        tile_row_exp_blk<false, kPolyEvery, 22, kHN / 2>(cur, p, kc, m_used, kHN, ls);
+        tile_row_exp_blk<false, kPolyEvery, kFb, kHN / 2>(cur, p, kc, m_used, kHN, ls);
         fold_sums(ls, kc);
       } else {
-        tile_row_exp<kInt8, false, kPolyEvery, 22, kHN / 2>(cur, p, c, m_used, kHN, lsum);
+        tile_row_exp<kInt8, false, kPolyEvery, kFb, kHN / 2>(cur, p, c, m_used, kHN, lsum);
       }
       if (tracer) tr[i * 4 + 2] = clock64();
       publish(i, p);
@@ -776,7 +777,7 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
   return true;
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 20, int kFb = 28>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD>;
   const uint64_t units = (uint64_t)a.B * a.H;
@@ -785,7 +786,7 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
       !make_map_2d(&tk, a.Kp, C::kEltQK, units * a.n_pad, kD, kBN, C::kAtomQK / C::kEltQK, err) ||
       !make_map_2d(&tv, a.Vt, 2, units * kD, a.n_pad, kD, 64, err))
     return false;
-  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace>;
+  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb>;
   {  // per device (context) attribute; cheap enough to set on every launch
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);

@@ -50,7 +50,8 @@ def clocks_between(t0, t1):
 
 for kern in ("int8", "f16"):
     if kern == "int8":
-        Qp, Kp, Vt, sc = qm.quantize_qkv(tq, tk, tv, H)
+        GR = qm.GRAN_BLOCK if os.environ.get("TUNE_BLOCK") else qm.GRAN_HEAD
+        Qp, Kp, Vt, sc = qm.quantize_qkv(tq, tk, tv, H, GR)
     else:
         Qp, Kp, Vt = qm.convert_qkv_f16(tq, tk, tv, H)
         sc = None
@@ -59,7 +60,7 @@ for kern in ("int8", "f16"):
         os.environ["QMHA_ATTN_VARIANT"] = str(v)
         try:
             for _ in range(2):
-                qm.attention_prepared(Qp, Kp, Vt, sc, B, N, dm, H, kern, out=out)
+                qm.attention_prepared(Qp, Kp, Vt, sc, B, N, dm, H, kern, out=out, gran=(GR if kern == "int8" else qm.GRAN_HEAD))
             torch.cuda.synchronize()
             qm.binding.check_async_error()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -67,7 +68,7 @@ for kern in ("int8", "f16"):
             w0 = time.time()
             e0.record()
             for _ in range(reps):
-                qm.attention_prepared(Qp, Kp, Vt, sc, B, N, dm, H, kern, out=out)
+                qm.attention_prepared(Qp, Kp, Vt, sc, B, N, dm, H, kern, out=out, gran=(GR if kern == "int8" else qm.GRAN_HEAD))
             e1.record()
             torch.cuda.synchronize()
             w1 = time.time()
