@@ -1,7 +1,7 @@
 """Block-scale mode probe: quantiser bit-exactness vs the oracle, attention vs emulated/FP, timing."""
 import os, sys, json
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import quantizedmha_b200 as qm
 from oracle import load_oracle

@@ -1,7 +1,7 @@
 """Tiny correctness probe for a kernel variant (QMHA_ATTN_VARIANT) with small shapes first."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import quantizedmha_b200 as qm
 from oracle import load_oracle
