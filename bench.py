@@ -262,21 +262,24 @@ def run_native(args):
     attn_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
     ms_step = total_ms / K
 
-    # ---- e2e: host buffers through the C-ABI, H2D + compute + D2H inside the timed region
+    # ---- e2e: host buffers through the C-ABI, H2D + compute + D2H inside the timed region.
+    # Pinned host memory is capped at ~8.6 GB: larger workloads (c5) time the first `Be` batch
+    # entries — the path pipelines per batch entry, so the rate is the same — and say so.
     e2e_steps = max(1, min(K, args.e2e_steps))
-    hq = torch.empty((Bl, N, dm), dtype=torch.float32, pin_memory=True)
+    Be = max(1, min(Bl, int(8.6e9 // (4 * N * dm * 4))))
+    hq = torch.empty((Be, N, dm), dtype=torch.float32, pin_memory=True)
     hk = torch.empty_like(hq, pin_memory=True)
     hv = torch.empty_like(hq, pin_memory=True)
     ho = torch.empty_like(hq, pin_memory=True)
-    hq.copy_(tq); hk.copy_(tk); hv.copy_(tv)
+    hq.copy_(tq[:Be]); hk.copy_(tk[:Be]); hv.copy_(tv[:Be])
     torch.cuda.synchronize()
-    chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Bl, N, dm, H, kid, gran))
+    chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Be, N, dm, H, kid, gran))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Bl, N, dm, H, kid, gran))
-    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-    e2e_maxdiff = float((ho.to(dev) - out).abs().max().item())
+        chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Be, N, dm, H, kid, gran))
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3 * (Bl / Be)   # scaled to the full per-rank batch
+    e2e_maxdiff = float((ho.to(dev) - out[:Be]).abs().max().item())
 
     t = torch.tensor([ms_step, attn_ms, prep_ms, e2e_ms], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -304,7 +307,7 @@ def run_native(args):
         "dtype": "s8*s8->s32 (Q.K^T), f16*f16->f32 (P.V), f32 softmax" if kernel == "int8" else "f16*f16->f32, f32 softmax",
         "data": "synthetic U[0,1) (inputs/data.cu distribution), random on device",
         "config": {"workload": f"{args.workload}: B={B}{' per GPU' if scaling == 'weak' and world > 1 else ''} H={H} N={N} d={d} "
-                               f"kernel={kernel} scales={args.scales}", "l2": "inputs (4.3 GB at c4) larger than the 126 MB L2",
+                               f"kernel={kernel} scales={args.scales}", "l2": f"inputs+outputs {4 * Bl * N * dm * 4 / 1e9:.2f} GB per GPU vs 126 MB L2 (no flush needed when larger)",
                    "parallelism": f"(batch x head) units sharded over {world} GPU(s), no collective"},
         "attn_ms": attn_ms, "attn_tflops_per_gpu": attn_tflops, "prep_ms": prep_ms,
         "prep_gbs_algorithmic": prep_bytes / (prep_ms / 1e3) / 1e9, "prep_frac_of_hbm": prep_bytes / (prep_ms / 1e3) / 1e9 / pk["hbm"],
@@ -316,6 +319,7 @@ def run_native(args):
                      "frac_of_nominal_mixed_3000": attn_tflops / 3000.0},
         "e2e": {"value": flops_all / (e2e_ms / 1e3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 3 * E * 4, "d2h_bytes_per_step": E * 4, "steps": e2e_steps,
+                "timed_batch_entries": Be, "of_batch_entries": Bl,
                 "api": "qmha_forward_host (pinned host buffers, copies pipelined per batch entry)",
                 "max_abs_vs_device_path": e2e_maxdiff},
         "gpu_launches": int(launches),
