@@ -12,9 +12,10 @@
 //   * warp 8 (one elected lane) issues every tcgen05.mma:  S_t[b] = Q_t·K_half^T  (kind::i8,
 //     int32 accumulators in TMEM — kind::f16 for the FP16 variant) into a DOUBLE-BUFFERED score
 //     tile, and  O_t += P_t[b]·V_half  (kind::f16, A operand = P read straight from TMEM,
-//     B = V^T tile in shared memory).  S_t for half-step i+2 is issued right behind P·V of
-//     half-step i, so the softmax warps always find their next scores waiting: the tensor-core
-//     round trip is off the softmax critical path;
+//     B = V^T tile in shared memory).  P_t(i) is written over the score buffer of half-step i+1
+//     (already copied to registers by then), so S_t for half-step i+3 can be issued right behind
+//     P·V of half-step i: scores are ready more than a full step before the softmax warps ask
+//     for them and the tensor-core round trip is off the softmax critical path;
 //   * warps 0-3 / 4-7 are the softmax warpgroups of tile 0 / tile 1: one thread per query row,
 //     S read with tcgen05.ld, dequant scale folded into the exponent FMA (packed FFMA2), exp2
 //     on the MUFU with an optional share on the FMA pipe (Cody-Waite + cubic polynomial), P
@@ -22,8 +23,11 @@
 //     only when the row max grows by more than 2^4;
 //   * epilogue: O·(sV/l) from TMEM to global memory in the reference's [N, h·d] layout.
 //
-// TMEM plan (512 columns): S0[0]|P0[0] = [0,64)  S0[1]|P0[1] = [64,128)  S1[0] = [128,192)
-//                          S1[1] = [192,256)  O0 = [256,384)  O1 = [384,512).
+// TMEM plan (512 columns): S0[0] = [0,64)  S0[1] = [64,128)  S1[0] = [128,192)  S1[1] = [192,256)
+//                          O0 = [256,384)  O1 = [384,512);  S_t(j) lives in S_t[j&1], P_t(i) in the
+//                          first 32 columns of S_t[(i+1)&1].
+#include <cstdlib>
+#include <type_traits>
 #include "attn_fwd.cuh"
 #include "sm100_ptx.cuh"
 
@@ -38,6 +42,7 @@ constexpr int kBN = 128;        // keys per KV tile in shared memory (one TMA st
 constexpr int kHN = 64;         // keys per half-step == UMMA N of Q·K^T, UMMA K extent of P·V
 constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
+constexpr int kTmaWarpV = 10;
 constexpr int kThreads = 384;            // 2 softmax warpgroups + 1 service warpgroup (MMA, TMA, 2 idle)
 constexpr int kRegsSoftmax = 208;        // setmaxnreg budgets: 2*128*208 + 128*72 = 62464 <= 65536
 constexpr int kRegsService = 72;
@@ -60,12 +65,19 @@ struct Cfg {
   static constexpr int kSubBytesV = kD * 128;                           // 64 keys x kD rows
   static constexpr int kStepsPV = kHN / 16;                             // UMMA K steps per half-step
   static constexpr int kHalfBytesQK = kHN * kAtomQK;                    // byte offset of K rows 64.. in a sub-tile
-  static constexpr int kBudget = 200 * 1024 - 2 * kTileBytesQK;
-  static constexpr int kStagesRaw = kBudget / (kTileBytesQK + kTileBytesV);
-  static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;       // K and V ring depth
-  static_assert(kStages >= 2, "need at least double buffering");
-  static constexpr int kSmemTiles = 2 * kTileBytesQK + kStages * (kTileBytesQK + kTileBytesV);
-  static constexpr int kSmemBytes = kSmemTiles + 1024 /*align slack*/ + 256 /*barriers*/;
+  // K tiles are consumed 1.5 tiles ahead of V tiles (S runs three half-steps ahead of P·V), so the
+  // K ring is one stage deeper than the V ring; each ring has its own producer warp.
+  static constexpr int kBudget = 224 * 1024 - 2 * kTileBytesQK;
+  static constexpr int kStagesRaw = (kBudget - kTileBytesQK) / (kTileBytesQK + kTileBytesV);
+  static constexpr int kStagesV = kStagesRaw > 3 ? 3 : kStagesRaw;
+#ifdef QMHA_EXP_K3
+  static constexpr int kStagesK = kStagesV;
+#else
+  static constexpr int kStagesK = kStagesV + 1;
+#endif
+  static_assert(kStagesV >= 2, "need at least double buffering");
+  static constexpr int kSmemTiles = 2 * kTileBytesQK + kStagesK * kTileBytesQK + kStagesV * kTileBytesV;
+  static constexpr int kSmemBytes = kSmemTiles + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr uint32_t kIdescQK =
       kInt8 ? make_idesc(kAccS32, kFmtS8, kFmtS8, kBM, kHN)
             : make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kHN);
@@ -76,12 +88,13 @@ struct Barriers {
   uint64_t q_full;
   uint64_t k_full[4], k_empty[4];
   uint64_t v_full[4], v_empty[4];
-  uint64_t s_full[2][2], p_full[2][2], pv_done[2];  // [tile][buffer]
+  uint64_t s_full[2][2], p_full[2][2], pv_done[2][2];  // [tile][buffer / step parity]
   uint64_t o_final[2];                              // one-shot: last P·V of the tile retired
+  uint64_t s0_read[2];                              // one-shot: S_t(0) copied to registers
   uint32_t tmem_base;
   uint32_t pad;
 };
-static_assert(sizeof(Barriers) <= 256, "barrier block too large");
+static_assert(sizeof(Barriers) <= 512, "barrier block too large");
 
 // Bounded mbarrier wait.  A healthy wait is microseconds; after ~1e9 cycles (or as soon as any
 // CTA has raised the global error flag) the wait gives up, records the site and lets the CTA
@@ -92,8 +105,11 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0) {
+#ifndef QMHA_WAIT_HINT_NS
+#define QMHA_WAIT_HINT_NS 20000
+#endif
+  while (!mbar_try_wait_hint(bar, parity, QMHA_WAIT_HINT_NS)) {
+    if ((++spins & 0xFu) == 0) {
       if (clock64() - t0 > 1000000000LL || *((volatile int*)err_flag) != 0) {
         atomicCAS(err_flag, 0, site);
         dead = true;
@@ -250,6 +266,10 @@ __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t 
 struct StepConsts {
   float c0, c1, lr0, lr1, ir0, ir1;
 };
+template <int B_, int E_>
+struct Range {
+  static constexpr int kB = B_, kE = E_;
+};
 
 template <bool kMasked>
 __device__ __forceinline__ float tile_row_max_blk(uint32_t (&s)[kHN], float c0, float c1, int n_valid) {
@@ -301,7 +321,7 @@ __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint3
   }
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 20, int kFb = 28>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 8, int kFb = 24>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, AttnParams prm) {
@@ -312,8 +332,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 2 * C::kTileBytesQK;
-  uint8_t* sV = sK + C::kStages * C::kTileBytesQK;
-  Barriers* bars = reinterpret_cast<Barriers*>(sV + C::kStages * C::kTileBytesV);
+  uint8_t* sV = sK + C::kStagesK * C::kTileBytesQK;
+  Barriers* bars = reinterpret_cast<Barriers*>(sV + C::kStagesV * C::kTileBytesV);
+  float4* blk_tab = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 512);  // block mode only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -330,7 +351,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     prefetch_tmap(&tm_k);
     prefetch_tmap(&tm_v);
     mbar_init(&bars->q_full, 1);
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->k_full[i], 1);
       mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1);
@@ -340,9 +361,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars->s_full[t][b], 1);
         mbar_init(&bars->p_full[t][b], 128);
+        mbar_init(&bars->pv_done[t][b], 1);
       }
-      mbar_init(&bars->pv_done[t], 1);
       mbar_init(&bars->o_final[t], 1);
+      mbar_init(&bars->s0_read[t], 128);
     }
     fence_mbar_init();
   }
@@ -360,7 +382,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
    // final barrier) so ptxas allocates registers per role.
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsService));
    if (warp == kTmaWarp) {
-    // ======================================================================== TMA producer
+    // ======================================================================== TMA producer: Q, K ring
     if (lane == 0) {
       const int q_row = unit * prm.n_pad + q_base;
       mbar_arrive_expect_tx(&bars->q_full, 2 * C::kTileBytesQK);
@@ -371,17 +393,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tma_load_2d(sQ + t * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_q, &bars->q_full,
                       sub * (C::kAtomQK / C::kEltQK), q_row + t * kBM);
       const int k_row0 = unit * prm.n_pad;
-      const int v_row = unit * kD;
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % C::kStages;
-        const uint32_t ph = (uint32_t)(j / C::kStages);
-        if (j >= C::kStages) mbar_wait(&bars->k_empty[st], (ph - 1) & 1, err_flag, 101, dead);
+        const int st = j % C::kStagesK;
+        const uint32_t ph = (uint32_t)(j / C::kStagesK);
+        if (j >= C::kStagesK) mbar_wait(&bars->k_empty[st], (ph - 1) & 1, err_flag, 101, dead);
         mbar_arrive_expect_tx(&bars->k_full[st], C::kTileBytesQK);
 #pragma unroll
         for (int sub = 0; sub < C::kSubQK; ++sub)
           tma_load_2d(sK + st * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_k, &bars->k_full[st],
                       sub * (C::kAtomQK / C::kEltQK), k_row0 + j * kBN);
-        if (j >= C::kStages) mbar_wait(&bars->v_empty[st], (ph - 1) & 1, err_flag, 102, dead);
+      }
+    }
+   } else if (warp == kTmaWarpV) {
+    // ======================================================================== TMA producer: V^T ring
+    if (lane == 0) {
+      const int v_row = unit * kD;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % C::kStagesV;
+        const uint32_t ph = (uint32_t)(j / C::kStagesV);
+        if (j >= C::kStagesV) mbar_wait(&bars->v_empty[st], (ph - 1) & 1, err_flag, 102, dead);
         mbar_arrive_expect_tx(&bars->v_full[st], C::kTileBytesV);
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub)
@@ -397,6 +427,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     {
       const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
       const bool leader = elect_one() != 0;
+      const bool do_mma = leader && !prm.debug_no_mma;
       // S_t[buf] = Q_t · K(stage st, key half `half`)^T
       auto issue_qk = [&](int t, int buf, int st, int half) {
         const uint32_t d_tmem = tmem_base + (t ? kColS1 : kColS0) + buf * kHN;
@@ -407,21 +438,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint64_t a = make_smem_desc(sQ_a + t * C::kTileBytesQK + off, C::kAtomQK);
           const uint64_t b = make_smem_desc(
               sK_a + st * C::kTileBytesQK + off + half * C::kHalfBytesQK, C::kAtomQK);
-          if (leader) {
+          if (do_mma) {
             if constexpr (kInt8) mma_i8_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
             else mma_f16_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
           }
         }
       };
-      // O_t (+)= P_t[buf] · V(stage st, key half `half`)
-      auto issue_pv = [&](int t, int buf, int st, int half, bool accumulate) {
+      // O_t (+)= P_t · V(stage st, key half `half`);  P_t sits in the first 32 columns of S_t[pbuf]
+      auto issue_pv = [&](int t, int pbuf, int st, int half, bool accumulate) {
         const uint32_t d_tmem = tmem_base + (t ? kColO1 : kColO0);
-        const uint32_t p_tmem = tmem_base + (t ? kColS1 : kColS0) + buf * kHN;
+        const uint32_t p_tmem = tmem_base + (t ? kColS1 : kColS0) + pbuf * kHN;
 #pragma unroll
         for (int ks = 0; ks < C::kStepsPV; ++ks) {
           const uint32_t off = (uint32_t)half * C::kSubBytesV + (uint32_t)ks * 32;
           const uint64_t b = make_smem_desc(sV_a + st * C::kTileBytesV + off, 128);
-          if (leader) mma_f16_ts(d_tmem, p_tmem + ks * 8, b, C::kIdescPV, (accumulate || ks > 0) ? 1u : 0u);
+          if (do_mma) mma_f16_ts(d_tmem, p_tmem + ks * 8, b, C::kIdescPV, (accumulate || ks > 0) ? 1u : 0u);
         }
       };
 
@@ -431,53 +462,66 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(&bars->k_full[0], 0, err_flag, 202, dead);
       tc_fence_after();
       __syncwarp();
-      // prologue: scores of half-steps 0 and 1 for both query tiles
+      // prologue: scores of half-steps 0 and 1 for both query tiles ...
       for (int t = 0; t < 2; ++t)
         for (int i = 0; i < 2 && i < n_half; ++i) {
           issue_qk(t, i, 0, i);
           commit(&bars->s_full[t][i]);
         }
       commit(&bars->k_empty[0]);
+      // ... and of half-step 2 as soon as the softmax warps have copied S(0) out of buffer 0
+      if (n_half > 2) {
+        const int st2 = 1 % C::kStagesK;
+        mbar_wait(&bars->k_full[st2], 0, err_flag, 207, dead);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&bars->s0_read[t], 0, err_flag, 208, dead);
+          tc_fence_after();
+          issue_qk(t, 0, st2, 0);
+          commit(&bars->s_full[t][0]);
+        }
+        if (n_half == 3) commit(&bars->k_empty[st2]);
+      }
 
+      // steady state, half-step i: O_t += P_t(i)·V(i), then S_t(i+3) into the buffer P_t(i) just left
       for (int i = 0; i < n_half; ++i) {
         const int j = i >> 1, half = i & 1;
-        const int st = j % C::kStages;
-        const uint32_t ph = (uint32_t)(j / C::kStages) & 1;
-        const uint32_t pbuf = (uint32_t)(i >> 1) & 1;   // parity of the [t][half] barriers
-        const int in = i + 2, jn = in >> 1;
-        const int stn = jn % C::kStages;
-        const uint32_t phn = (uint32_t)(jn / C::kStages) & 1;
+        const int st = j % C::kStagesV;
+        const uint32_t ph = (uint32_t)(j / C::kStagesV) & 1;
+        const uint32_t pbar = (uint32_t)(i >> 1) & 1;   // parity of the p_full[t][i&1] barriers
+        const int in = i + 3, jn = in >> 1, halfn = in & 1;
+        const int stn = jn % C::kStagesK;
+        const uint32_t phn = (uint32_t)(jn / C::kStagesK) & 1;
         const bool more = in < n_half;
         long long* trm = kTrace ? prm.trace + (size_t)2 * n_half * 4 + (size_t)i * 4 : nullptr;
         const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
 
         if (half == 0) mbar_wait(&bars->v_full[st], ph, err_flag, 203, dead);
-        mbar_wait(&bars->p_full[0][half], pbuf, err_flag, 204, dead);
+        mbar_wait(&bars->p_full[0][half], pbar, err_flag, 204, dead);
         tc_fence_after();
         if (tracer) trm[0] = clock64();
-        issue_pv(0, half, st, half, i > 0);
-        commit(&bars->pv_done[0]);
+        issue_pv(0, (i + 1) & 1, st, half, i > 0);
+        commit(&bars->pv_done[0][half]);
         if (i == n_half - 1) commit(&bars->o_final[0]);
         if (more) {
-          if (half == 0) {
+          if (halfn == 0) {
             mbar_wait(&bars->k_full[stn], phn, err_flag, 205, dead);
             tc_fence_after();
           }
-          issue_qk(0, half, stn, half);
-          commit(&bars->s_full[0][half]);
+          issue_qk(0, in & 1, stn, halfn);
+          commit(&bars->s_full[0][in & 1]);
         }
         if (tracer) trm[1] = clock64();
-        mbar_wait(&bars->p_full[1][half], pbuf, err_flag, 206, dead);
+        mbar_wait(&bars->p_full[1][half], pbar, err_flag, 206, dead);
         tc_fence_after();
         if (tracer) trm[2] = clock64();
-        issue_pv(1, half, st, half, i > 0);
-        commit(&bars->pv_done[1]);
+        issue_pv(1, (i + 1) & 1, st, half, i > 0);
+        commit(&bars->pv_done[1][half]);
         if (i == n_half - 1) commit(&bars->o_final[1]);
         if (half == 1 || i == n_half - 1) commit(&bars->v_empty[st]);
         if (more) {
-          issue_qk(1, half, stn, half);
-          commit(&bars->s_full[1][half]);
-          if (half == 1 || in == n_half - 1) commit(&bars->k_empty[stn]);
+          issue_qk(1, in & 1, stn, halfn);
+          commit(&bars->s_full[1][in & 1]);
+          if (halfn == 1 || in == n_half - 1) commit(&bars->k_empty[stn]);
         }
         if (tracer) trm[3] = clock64();
       }
@@ -515,20 +559,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0;
     long long* tr = kTrace ? prm.trace + (size_t)t * n_half * 4 : nullptr;
 
-    // The softmax loop is software-pipelined over half-steps: while the exponentials of step i
-    // run, the scores of step i+1 (already computed by the tensor core: S is double-buffered)
-    // are fetched from TMEM and their row max is taken, so tcgen05.ld latency and the max
-    // dependency chain hide under the MUFU work.  Two register arrays (sA, sB) alternate.
+    // block mode: per-32-key-block constants {sK, log2 r, 1/r, -} of this unit staged in shared memory
+    // once per CTA (256 softmax threads), so the per-step lookups are two broadcast LDS.128.
+    if constexpr (kBlk) {
+      const float* gk = prm.blk_scales + ((size_t)prm.units + unit) * nblk;
+      const float2* ga = reinterpret_cast<const float2*>(prm.blk_aux) + (size_t)unit * nblk;
+      for (int g = threadIdx.x; g < nblk; g += 256) {
+        const float2 a = __ldg(ga + g);
+        blk_tab[g] = make_float4(__ldg(gk + g), a.x, a.y, 0.f);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
 
-    // block mode: scale factors of the two 32-key blocks of half-step i (broadcast loads)
+    // The softmax loop is software-pipelined over half-steps.  While the exponentials of step i
+    // run, (1) P(i-1) — finished at the end of the previous step — is stored to TMEM and handed
+    // to the MMA warp (kP pairs into the step, so the MUFU queue never drains across the step
+    // boundary), (2) the scores of step i+1 (ready long ago: S runs three half-steps ahead) are
+    // fetched from TMEM, their row max is taken and the warp votes whether step i+1 must raise
+    // the reference max.  Two register arrays for S (sA, sB) and for P (pA, pB) alternate.
     auto load_consts = [&](int i) {
       StepConsts k{c, c, 0.f, 0.f, 1.f, 1.f};
       if constexpr (kBlk) {
-        const float* sk = prm.blk_scales + ((size_t)prm.units + unit) * nblk + 2 * i;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(prm.blk_aux + ((size_t)unit * nblk + 2 * i) * 2));
-        k.c0 = c * __ldg(sk);
-        k.c1 = c * __ldg(sk + 1);
-        k.lr0 = a.x; k.ir0 = a.y; k.lr1 = a.z; k.ir1 = a.w;
+        const float4 a = blk_tab[2 * i], b = blk_tab[2 * i + 1];
+        k.c0 = c * a.x; k.lr0 = a.y; k.ir0 = a.z;
+        k.c1 = c * b.x; k.lr1 = b.y; k.ir1 = b.z;
       }
       return k;
     };
@@ -546,140 +600,157 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       unpack2(ls[1], b0, b1);
       l_acc = fmaf(a0 + a1, k.ir0, fmaf(b0 + b1, k.ir1, l_acc));
     };
+    // exponentials of pairs [kBegin, kEnd) of an unmasked step
+    auto exps = [&](auto range, const uint32_t (&sx)[kHN], uint32_t (&p)[kHN / 2], const StepConsts& k,
+                    uint64_t (&ls)[2]) {
+      constexpr int kB = decltype(range)::kB, kE = decltype(range)::kE;
+      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, kB, kE>(sx, p, k, m_used, kHN, ls);
+      else tile_row_exp<kInt8, false, kPolyEvery, kB, kE>(sx, p, c, m_used, kHN, lsum);
+    };
 
     // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld)
     auto fetch = [&](int i, uint32_t (&dst)[kHN]) {
       const int buf = i & 1;
       mbar_wait(&bars->s_full[t][buf], (uint32_t)(i >> 1) & 1, err_flag, 301 + t, dead);
-      dead = __any_sync(0xffffffffu, dead);
       tc_fence_after();
       tmem_ld32(tS + buf * kHN, &dst[0]);
       tmem_ld32(tS + buf * kHN + 32, &dst[32]);
     };
-    // lazy max update (+ rare rescale of O and l) for step i given the step's row max `mt`.
-    // Keeps the old reference max unless the new one is more than 2^kRescaleThreshold larger.
-    // The decision is made warp-uniform because tcgen05.ld/st are warp collectives.
-    auto update_max = [&](int i, float mt) {
-      const bool need = mt > m_used + kRescaleThreshold;
-      if (__any_sync(0xffffffffu, need)) {
-        const float m_new = need ? mt : m_used;
-        if (i > 0) {
-          const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
-          const uint64_t alpha2 = pack2(alpha, alpha);
-          lsum[0] = fmul2(lsum[0], alpha2);
-          lsum[1] = fmul2(lsum[1], alpha2);
-          l_acc *= alpha;
-          mbar_wait(&bars->pv_done[t], (i - 1) & 1, err_flag, 311 + t, dead);
-          dead = __any_sync(0xffffffffu, dead);
-          tc_fence_after();
-#pragma unroll
-          for (int ch = 0; ch < kD / 32; ++ch) {
-            uint32_t o[32];
-            tmem_ld32(tO + ch * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
-            tmem_st32(tO + ch * 32, o);
-          }
-          tmem_wait_st();
-        }
-        m_used = m_new;
-      }
-    };
-    // P_t(i) -> TMEM (over the S buffer it came from), then tell the MMA warp.
+    // P_t(i) -> TMEM, over the score buffer of step i+1 (its scores are in registers by now),
+    // then tell the MMA warp.
     auto publish = [&](int i, const uint32_t (&p)[kHN / 2]) {
-      const int buf = i & 1;
-      tmem_st32(tS + buf * kHN, &p[0]);
+      tmem_st32(tS + ((i + 1) & 1) * kHN, &p[0]);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->p_full[t][buf]);
+      mbar_arrive(&bars->p_full[t][i & 1]);
       if (tracer) tr[i * 4 + 3] = clock64();
     };
-    // pipelined step: exp of `cur` (step i, unmasked) overlapped with fetch + max of step i+1.
-    auto pipe_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur, const StepConsts& kc,
-                         uint32_t (&nxt)[kHN], float& mt_nxt, StepConsts& kn) {
-      if (tracer) tr[i * 4 + 0] = clock64();
-      update_max(i, mt_cur);
-      uint32_t p[kHN / 2];
-      uint64_t ls[2] = {0ull, 0ull};
-      // S_t(i+1) is issued behind P·V of step i-1, i.e. it lands roughly half way into this step:
-      // run kFa of the 32 exponential pairs first so the fetch does not stall on it, take the row
-      // max of the fetched scores after kFb pairs (measured best of several placements: 20 / 28).
-      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, 0, kFa>(cur, p, kc, m_used, kHN, ls);
-      else tile_row_exp<kInt8, false, kPolyEvery, 0, kFa>(cur, p, c, m_used, kHN, lsum);
-      fetch(i + 1, nxt);
-      kn = load_consts(i + 1);
-      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, kFa, kFb>(cur, p, kc, m_used, kHN, ls);
-      else tile_row_exp<kInt8, false, kPolyEvery, kFa, kFb>(cur, p, c, m_used, kHN, lsum);
-      tmem_wait_ld();
-      mt_nxt = row_max(nxt, kn, false, kHN);
-      if constexpr (kBlk) {
-        tile_row_exp_blk<false, kPolyEvery, kFb, kHN / 2>(cur, p, kc, m_used, kHN, ls);
-        fold_sums(ls, kc);
-      } else {
-        tile_row_exp<kInt8, false, kPolyEvery, kFb, kHN / 2>(cur, p, c, m_used, kHN, lsum);
+    // Raise the reference max for step i (and, for i > 0, rescale l and the O rows in TMEM).
+    // Called only when the warp voted for it: the old max is kept unless the new row max exceeds
+    // it by more than 2^kRescaleThreshold.  P(i-1) must have been published before.
+    auto raise_max = [&](int i, float mt) {
+      const bool need = mt > m_used + kRescaleThreshold;
+      const float m_new = need ? mt : m_used;
+      if (i > 0) {
+        const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
+        const uint64_t alpha2 = pack2(alpha, alpha);
+        lsum[0] = fmul2(lsum[0], alpha2);
+        lsum[1] = fmul2(lsum[1], alpha2);
+        l_acc *= alpha;
+        // P·V(i-1) retired?  (one barrier per step parity: P·V(i-3) is known to be complete, so
+        // the phase cannot alias)
+        mbar_wait(&bars->pv_done[t][(i - 1) & 1], (uint32_t)((i - 1) >> 1) & 1, err_flag, 311 + t, dead);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < kD / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
+          tmem_st32(tO + ch * 32, o);
+        }
+        tmem_wait_st();
       }
-      if (tracer) tr[i * 4 + 2] = clock64();
-      publish(i, p);
+      m_used = m_new;
     };
-    // step whose scores are already in registers, nothing left to prefetch (unmasked).
-    auto drain_step = [&](int i, uint32_t (&cur)[kHN], float mt_cur, const StepConsts& kc) {
+    auto vote_raise = [&](float mt) { return __any_sync(0xffffffffu, mt > m_used + kRescaleThreshold) != 0; };
+
+    // One pipelined step i < n_half-1 (always unmasked): exponentials of `cur` into `p`; publishes
+    // `p_prev` = P(i-1) (if i > 0); if kPrefetch, fetches S(i+1) (unmasked, i.e. i+1 < n_half-1)
+    // into `nxt` with row max and vote.
+    auto pipe_step = [&](auto prefetch, int i, uint32_t (&cur)[kHN], float mt_cur, bool raise_cur,
+                         const StepConsts& kc, uint32_t (&p)[kHN / 2], const uint32_t (&p_prev)[kHN / 2],
+                         uint32_t (&nxt)[kHN], float& mt_nxt, bool& raise_nxt, StepConsts& kn) {
+      constexpr bool kPrefetch = decltype(prefetch)::value;
       if (tracer) tr[i * 4 + 0] = clock64();
-      update_max(i, mt_cur);
-      uint32_t p[kHN / 2];
+      bool published = i == 0;
+      if (raise_cur) {  // rare after the first steps
+        if (!published) publish(i - 1, p_prev);
+        published = true;
+        raise_max(i, mt_cur);
+      }
+      uint64_t ls[2] = {0ull, 0ull};
+      exps(Range<0, kFa>{}, cur, p, kc, ls);
+      if (!published) publish(i - 1, p_prev);
+      if constexpr (kPrefetch) {
+        fetch(i + 1, nxt);
+        kn = load_consts(i + 1);
+        exps(Range<kFa, kFb>{}, cur, p, kc, ls);
+        tmem_wait_ld();
+        mt_nxt = row_max(nxt, kn, false, kHN);
+        raise_nxt = vote_raise(mt_nxt);
+        exps(Range<kFb, kHN / 2>{}, cur, p, kc, ls);
+      } else {
+        exps(Range<kFa, kHN / 2>{}, cur, p, kc, ls);
+      }
+      if constexpr (kBlk) fold_sums(ls, kc);
+      if (tracer) tr[i * 4 + 2] = clock64();
+    };
+    // last step (i == n_half-1): may cover fewer than 64 existing keys; not pipelined
+    auto last_step = [&](int i, uint32_t (&cur)[kHN], uint32_t (&p)[kHN / 2], const uint32_t (&p_prev)[kHN / 2]) {
+      if (tracer) tr[i * 4 + 0] = clock64();
+      fetch(i, cur);
+      const StepConsts kl = load_consts(i);
+      const int n_valid = prm.N - i * kHN;  // >= 1
+      const bool masked = n_valid < kHN;
+      tmem_wait_ld();
+      if (i > 0) publish(i - 1, p_prev);  // P(i-1) goes over the S(i) buffer: only after the load
+      const float mt = row_max(cur, kl, masked, n_valid);
+      if (vote_raise(mt)) raise_max(i, mt);
       if constexpr (kBlk) {
         uint64_t ls[2] = {0ull, 0ull};
-        tile_row_exp_blk<false, kPolyEvery>(cur, p, kc, m_used, kHN, ls);
-        fold_sums(ls, kc);
+        if (masked) tile_row_exp_blk<true, kPolyEvery>(cur, p, kl, m_used, n_valid, ls);
+        else tile_row_exp_blk<false, kPolyEvery>(cur, p, kl, m_used, kHN, ls);
+        fold_sums(ls, kl);
       } else {
-        tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum);
+        if (masked) tile_row_exp<kInt8, true, kPolyEvery>(cur, p, c, m_used, n_valid, lsum);
+        else tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum);
       }
       if (tracer) tr[i * 4 + 2] = clock64();
+      // P(i) goes over P(i-2).  In the steady state the fetch of S(i+1) proves that P·V(i-2) has
+      // retired; there is no S(i+1) here, so ask the tensor pipe directly.
+      if (i >= 2) {
+        mbar_wait(&bars->pv_done[t][i & 1], (uint32_t)((i - 2) >> 1) & 1, err_flag, 331 + t, dead);
+        tc_fence_after();
+      }
       publish(i, p);
     };
+    using Yes = std::true_type;
+    using No = std::false_type;
 
-    uint32_t sA[kHN], sB[kHN];
+    uint32_t sA[kHN], sB[kHN], pA[kHN / 2], pB[kHN / 2];
     float mtA = 0.f, mtB = 0.f;
+    bool raiseA = true, raiseB = true;  // the first step always installs its row max
     StepConsts kA = load_consts(0), kB = kA;
     int i = 0;
     if (n_half >= 2) {
       // steps 0 .. n_half-2 are full (unmasked) by construction; only the last one can be ragged
       fetch(0, sA);
       tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&bars->s0_read[t]);  // buffer 0 is free for S(2)
       mtA = row_max(sA, kA, false, kHN);
       bool in_a = true;
       while (i + 2 < n_half) {
-        pipe_step(i, sA, mtA, kA, sB, mtB, kB);
+        pipe_step(Yes{}, i, sA, mtA, raiseA, kA, pA, pB, sB, mtB, raiseB, kB);
         ++i;
         if (!(i + 2 < n_half)) { in_a = false; break; }
-        pipe_step(i, sB, mtB, kB, sA, mtA, kA);
+        pipe_step(Yes{}, i, sB, mtB, raiseB, kB, pB, pA, sA, mtA, raiseA, kA);
         ++i;
       }
-      if (in_a) drain_step(i, sA, mtA, kA);
-      else drain_step(i, sB, mtB, kB);
-      ++i;
-    }
-    {
-      // last step (i == n_half-1): may cover fewer than 64 existing keys
-      if (tracer) tr[i * 4 + 0] = clock64();
-      fetch(i, sA);
-      const StepConsts kl = load_consts(i);
-      tmem_wait_ld();
-      const int n_valid = prm.N - i * kHN;  // >= 1
-      const bool masked = n_valid < kHN;
-      uint32_t p[kHN / 2];
-      update_max(i, row_max(sA, kl, masked, n_valid));
-      if constexpr (kBlk) {
-        uint64_t ls[2] = {0ull, 0ull};
-        if (masked) tile_row_exp_blk<true, kPolyEvery>(sA, p, kl, m_used, n_valid, ls);
-        else tile_row_exp_blk<false, kPolyEvery>(sA, p, kl, m_used, kHN, ls);
-        fold_sums(ls, kl);
+      // step n_half-2: nothing to prefetch (the last step fetches for itself)
+      if (in_a) {
+        pipe_step(No{}, i, sA, mtA, raiseA, kA, pA, pB, sB, mtB, raiseB, kB);
+        ++i;
+        last_step(i, sB, pB, pA);
       } else {
-        if (masked) tile_row_exp<kInt8, true, kPolyEvery>(sA, p, c, m_used, n_valid, lsum);
-        else tile_row_exp<kInt8, false, kPolyEvery>(sA, p, c, m_used, kHN, lsum);
+        pipe_step(No{}, i, sB, mtB, raiseB, kB, pB, pA, sA, mtA, raiseA, kA);
+        ++i;
+        last_step(i, sA, pA, pB);
       }
-      if (tracer) tr[i * 4 + 2] = clock64();
-      publish(i, p);
+    } else {
+      last_step(0, sA, pA, pB);
     }
 
     // ---------------------------------------------------------------- epilogue: O * sV / l
@@ -777,7 +848,7 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
   return true;
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 20, int kFb = 28>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 8, int kFb = 24>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD>;
   const uint64_t units = (uint64_t)a.B * a.H;
@@ -787,9 +858,15 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
       !make_map_2d(&tv, a.Vt, 2, units * kD, a.n_pad, kD, 64, err))
     return false;
   auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb>;
+  // block mode keeps one float4 of constants per 32-key block of the unit behind the barriers
+  const size_t smem_bytes = (size_t)C::kSmemBytes + (kBlk ? (size_t)(a.n_pad / 32) * 16 : 0);
+  if (smem_bytes > 227 * 1024) {
+    *err = "sequence too long for the per-block scale table in shared memory (use head granularity)";
+    return false;
+  }
   {  // per device (context) attribute; cheap enough to set on every launch
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
+                                         (int)smem_bytes);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
   }
   AttnParams p;
@@ -806,8 +883,9 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.n_kv_tiles = (a.N + kBN - 1) / kBN;
   p.n_half_steps = (a.N + kHN - 1) / kHN;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)a.d);
+  p.debug_no_mma = getenv("QMHA_DEBUG_NO_MMA") != nullptr;
   dim3 grid((a.N + 2 * kBM - 1) / (2 * kBM), (unsigned)units, 1);
-  kern<<<grid, kThreads, C::kSmemBytes, a.stream>>>(tq, tk, tv, p);
+  kern<<<grid, kThreads, smem_bytes, a.stream>>>(tq, tk, tv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("attention launch: ") + cudaGetErrorString(e); return false; }
   return true;

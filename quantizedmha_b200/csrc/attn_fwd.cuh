@@ -20,6 +20,7 @@ struct AttnParams {
   int n_kv_tiles;       // ceil(N / 128): K/V tiles staged by TMA
   int n_half_steps;     // ceil(N / 64): 64-key softmax/MMA half-steps
   float scale_log2;     // log2(e) / sqrt(d)
+  int debug_no_mma;     // measurement aid: skip every tcgen05.mma (results are garbage)
 };
 
 struct AttnLaunch {
