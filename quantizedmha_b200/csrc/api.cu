@@ -369,7 +369,7 @@ int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B
 }
 
 // Debug: runs the traced INT8 d=128 kernel once (synchronously) and copies the timeline of CTA
-// (0,0) to host_trace[3][ceil(N/64)][4] (clock64 stamps: softmax tile 0, softmax tile 1, MMA).
+// (0,0) to host_trace[9][ceil(N/64)][4] (clock64 stamps: softmax warps 0-7, MMA warp).
 int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* Vt,
                                const float* scales, float* O, int B, int N, int d_model, int h,
                                int variant, long long* host_trace) {
@@ -377,7 +377,7 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
   if (dev < 0) return 1;
   Workspace* w;
   if (get_workspace(dev, 0, 0, 0, &w)) return 1;
-  const size_t n = (size_t)3 * ((N + 63) / 64) * 4;
+  const size_t n = (size_t)9 * ((N + 63) / 64) * 4;
   long long* dtrace = nullptr;
   cudaError_t e = cudaMalloc(&dtrace, n * sizeof(long long));
   if (e != cudaSuccess) return fail_cuda("cudaMalloc(trace)", e);

@@ -40,9 +40,15 @@ namespace {
 constexpr int kBM = 128;        // query rows per tile == UMMA M
 constexpr int kBN = 128;        // keys per KV tile in shared memory (one TMA stage)
 constexpr int kHN = 64;         // keys per half-step == UMMA N of Q·K^T, UMMA K extent of P·V
-constexpr int kMmaWarp = 8;
+// Service warps 8..11 (one per SM sub-partition).  tcgen05.mma issue visibly slows the softmax
+// warps that share the issuing warp's sub-partition, so the issue work is split: with
+// kMmaSplit == 2, warp 8 issues everything for query tile 0 and warp 11 for tile 1 (warps 9 / 10
+// are the K / V TMA producers).
+constexpr int kMmaSplit = 2;
+constexpr int kAllocWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr int kTmaWarpV = 10;
+__host__ __device__ constexpr bool is_mma_warp(int warp) { return warp == 8 || warp == 11; }
 constexpr int kThreads = 384;            // 2 softmax warpgroups + 1 service warpgroup (MMA, TMA, 2 idle)
 constexpr int kRegsSoftmax = 208;        // setmaxnreg budgets: 2*128*208 + 128*72 = 62464 <= 65536
 constexpr int kRegsService = 72;
@@ -353,9 +359,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(&bars->q_full, 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->k_full[i], 1);
-      mbar_init(&bars->k_empty[i], 1);
+      mbar_init(&bars->k_empty[i], kMmaSplit);
       mbar_init(&bars->v_full[i], 1);
-      mbar_init(&bars->v_empty[i], 1);
+      mbar_init(&bars->v_empty[i], kMmaSplit);
     }
     for (int t = 0; t < 2; ++t) {
       for (int b = 0; b < 2; ++b) {
@@ -368,7 +374,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == kAllocWarp) {
     tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
   }
@@ -419,7 +425,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                       j * kBN + sub * 64, v_row);
       }
     }
-   } else if (warp == kMmaWarp) {
+   } else if (is_mma_warp(warp)) {
     // ======================================================================== MMA issuer
     // The whole warp runs this code with uniform control flow (so descriptors live in uniform
     // registers); only the tcgen05.mma / tcgen05.commit instructions are issued by one elected
@@ -428,16 +434,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
       const bool leader = elect_one() != 0;
       const bool do_mma = leader && !prm.debug_no_mma;
+      // Base descriptors are built once; per MMA only the 14-bit address field moves (one add).
+      const uint64_t q_desc0 = make_smem_desc(sQ_a, C::kAtomQK);
+      const uint64_t k_desc0 = make_smem_desc(sK_a, C::kAtomQK);
+      const uint64_t v_desc0 = make_smem_desc(sV_a, 128);
       // S_t[buf] = Q_t · K(stage st, key half `half`)^T
       auto issue_qk = [&](int t, int buf, int st, int half) {
         const uint32_t d_tmem = tmem_base + (t ? kColS1 : kColS0) + buf * kHN;
+        const uint64_t a0 = advance_smem_desc(q_desc0, (uint32_t)t * C::kTileBytesQK);
+        const uint64_t b0 = advance_smem_desc(k_desc0, (uint32_t)st * C::kTileBytesQK + (uint32_t)half * C::kHalfBytesQK);
 #pragma unroll
         for (int ks = 0; ks < C::kStepsQK; ++ks) {
+          constexpr int kDummy = 0; (void)kDummy;
           const uint32_t off = (uint32_t)((ks * 32) / C::kAtomQK) * C::kSubBytesQK +
                                (uint32_t)((ks * 32) % C::kAtomQK);
-          const uint64_t a = make_smem_desc(sQ_a + t * C::kTileBytesQK + off, C::kAtomQK);
-          const uint64_t b = make_smem_desc(
-              sK_a + st * C::kTileBytesQK + off + half * C::kHalfBytesQK, C::kAtomQK);
+          const uint64_t a = advance_smem_desc(a0, off);
+          const uint64_t b = advance_smem_desc(b0, off);
           if (do_mma) {
             if constexpr (kInt8) mma_i8_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
             else mma_f16_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
@@ -448,10 +460,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       auto issue_pv = [&](int t, int pbuf, int st, int half, bool accumulate) {
         const uint32_t d_tmem = tmem_base + (t ? kColO1 : kColO0);
         const uint32_t p_tmem = tmem_base + (t ? kColS1 : kColS0) + pbuf * kHN;
+        const uint64_t b0 = advance_smem_desc(v_desc0, (uint32_t)st * C::kTileBytesV + (uint32_t)half * C::kSubBytesV);
 #pragma unroll
         for (int ks = 0; ks < C::kStepsPV; ++ks) {
-          const uint32_t off = (uint32_t)half * C::kSubBytesV + (uint32_t)ks * 32;
-          const uint64_t b = make_smem_desc(sV_a + st * C::kTileBytesV + off, 128);
+          const uint64_t b = advance_smem_desc(b0, (uint32_t)ks * 32);
           if (do_mma) mma_f16_ts(d_tmem, p_tmem + ks * 8, b, C::kIdescPV, (accumulate || ks > 0) ? 1u : 0u);
         }
       };
@@ -459,70 +471,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       auto commit = [&](uint64_t* bar) { if (leader) mma_commit(bar); };
       const int n_half = prm.n_half_steps;
       mbar_wait(&bars->q_full, 0, err_flag, 201, dead);
-      mbar_wait(&bars->k_full[0], 0, err_flag, 202, dead);
       tc_fence_after();
       __syncwarp();
-      // prologue: scores of half-steps 0 and 1 for both query tiles ...
-      for (int t = 0; t < 2; ++t)
-        for (int i = 0; i < 2 && i < n_half; ++i) {
-          issue_qk(t, i, 0, i);
-          commit(&bars->s_full[t][i]);
-        }
-      commit(&bars->k_empty[0]);
-      // ... and of half-step 2 as soon as the softmax warps have copied S(0) out of buffer 0
-      if (n_half > 2) {
-        const int st2 = 1 % C::kStagesK;
-        mbar_wait(&bars->k_full[st2], 0, err_flag, 207, dead);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&bars->s0_read[t], 0, err_flag, 208, dead);
+      // This warp issues, for query tile `mt`, every half-step i with owns(i) — all of them when the
+      // work is split by tile only.  Half-step i means: O += P(i)·V(i), then S(i+3) into the score
+      // buffer P(i) just left; the scores of half-steps 0..2 belong to the owners of "steps" -3..-1.
+      const int mt = warp == 8 ? 0 : 1;
+      constexpr int kStride = kMmaSplit == 2 ? 1 : 2;
+      const int first = 0;
+      auto owns = [&](int step) { return kStride == 1 || (step & 1) == first; };
+      auto qk_step = [&](int in, int wait_site) {   // S_mt(in): wait for its K tile, issue, signal, release
+        const int jn = in >> 1, halfn = in & 1, stn = jn % C::kStagesK;
+        mbar_wait(&bars->k_full[stn], (uint32_t)(jn / C::kStagesK) & 1, err_flag, wait_site, dead);
+        tc_fence_after();
+        issue_qk(mt, in & 1, stn, halfn);
+        commit(&bars->s_full[mt][in & 1]);
+        // last read of this K tile by this warp: one arrival per MMA warp frees the stage
+        if (kStride == 2 || halfn == 1 || in == n_half - 1) commit(&bars->k_empty[stn]);
+      };
+      for (int in = 0; in < 3 && in < n_half; ++in) {
+        if (!owns(in - 3)) continue;
+        if (in == 2) {  // buffer 0 is reusable once the softmax warps hold S(0) in registers
+          mbar_wait(&bars->s0_read[mt], 0, err_flag, 208, dead);
           tc_fence_after();
-          issue_qk(t, 0, st2, 0);
-          commit(&bars->s_full[t][0]);
         }
-        if (n_half == 3) commit(&bars->k_empty[st2]);
+        qk_step(in, 202);
       }
-
-      // steady state, half-step i: O_t += P_t(i)·V(i), then S_t(i+3) into the buffer P_t(i) just left
-      for (int i = 0; i < n_half; ++i) {
+      for (int i = first; i < n_half; i += kStride) {
         const int j = i >> 1, half = i & 1;
         const int st = j % C::kStagesV;
-        const uint32_t ph = (uint32_t)(j / C::kStagesV) & 1;
-        const uint32_t pbar = (uint32_t)(i >> 1) & 1;   // parity of the p_full[t][i&1] barriers
-        const int in = i + 3, jn = in >> 1, halfn = in & 1;
-        const int stn = jn % C::kStagesK;
-        const uint32_t phn = (uint32_t)(jn / C::kStagesK) & 1;
-        const bool more = in < n_half;
-        long long* trm = kTrace ? prm.trace + (size_t)2 * n_half * 4 + (size_t)i * 4 : nullptr;
-        const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
-
-        if (half == 0) mbar_wait(&bars->v_full[st], ph, err_flag, 203, dead);
-        mbar_wait(&bars->p_full[0][half], pbar, err_flag, 204, dead);
+        long long* trm = kTrace ? prm.trace + (size_t)8 * n_half * 4 + (size_t)i * 4 : nullptr;
+        const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && mt == 0;
+        mbar_wait(&bars->v_full[st], (uint32_t)(j / C::kStagesV) & 1, err_flag, 203, dead);
+        mbar_wait(&bars->p_full[mt][half], (uint32_t)(i >> 1) & 1, err_flag, 204, dead);
+        if (kStride == 2 && i > 0)  // the other warp's P·V(i-1) must have retired before O is touched again
+          mbar_wait(&bars->pv_done[mt][(i - 1) & 1], (uint32_t)((i - 1) >> 1) & 1, err_flag, 209, dead);
         tc_fence_after();
         if (tracer) trm[0] = clock64();
-        issue_pv(0, (i + 1) & 1, st, half, i > 0);
-        commit(&bars->pv_done[0][half]);
-        if (i == n_half - 1) commit(&bars->o_final[0]);
-        if (more) {
-          if (halfn == 0) {
-            mbar_wait(&bars->k_full[stn], phn, err_flag, 205, dead);
-            tc_fence_after();
-          }
-          issue_qk(0, in & 1, stn, halfn);
-          commit(&bars->s_full[0][in & 1]);
-        }
+        issue_pv(mt, (i + 1) & 1, st, half, i > 0);
+        commit(&bars->pv_done[mt][half]);
+        if (i == n_half - 1) commit(&bars->o_final[mt]);
+        if (kStride == 2 || half == 1 || i == n_half - 1) commit(&bars->v_empty[st]);
         if (tracer) trm[1] = clock64();
-        mbar_wait(&bars->p_full[1][half], pbar, err_flag, 206, dead);
-        tc_fence_after();
-        if (tracer) trm[2] = clock64();
-        issue_pv(1, (i + 1) & 1, st, half, i > 0);
-        commit(&bars->pv_done[1][half]);
-        if (i == n_half - 1) commit(&bars->o_final[1]);
-        if (half == 1 || i == n_half - 1) commit(&bars->v_empty[st]);
-        if (more) {
-          issue_qk(1, in & 1, stn, halfn);
-          commit(&bars->s_full[1][in & 1]);
-          if (halfn == 1 || in == n_half - 1) commit(&bars->k_empty[stn]);
-        }
+        if (i + 3 < n_half) qk_step(i + 3, 205);
         if (tracer) trm[3] = clock64();
       }
     }
@@ -556,8 +547,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint64_t lsum[2] = {0ull, 0ull};  // four fp32 partial row sums (packed pairs); block mode: l_acc
     float l_acc = 0.f;
     const int n_half = prm.n_half_steps;
-    const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && (warp & 3) == 0 && lane == 0;
-    long long* tr = kTrace ? prm.trace + (size_t)t * n_half * 4 : nullptr;
+    // trace layout: [8 softmax warps + MMA][n_half][4]; softmax: step start, before / after the
+    // s_full wait of the prefetch, P(i) published
+    const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+    long long* tr = kTrace ? prm.trace + (size_t)warp * n_half * 4 : nullptr;
 
     // block mode: per-32-key-block constants {sK, log2 r, 1/r, -} of this unit staged in shared memory
     // once per CTA (256 softmax threads), so the per-step lookups are two broadcast LDS.128.
@@ -608,10 +601,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       else tile_row_exp<kInt8, false, kPolyEvery, kB, kE>(sx, p, c, m_used, kHN, lsum);
     };
 
-    // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld)
-    auto fetch = [&](int i, uint32_t (&dst)[kHN]) {
+    // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld).  `probed` is the
+    // result of an earlier non-blocking probe of the same barrier phase (keeps the barrier-unit round
+    // trip off the critical path when the scores are already there, which is the normal case).
+    auto probe = [&](int i) {
+      return mbar_test_wait(&bars->s_full[t][i & 1], (uint32_t)(i >> 1) & 1) != 0;
+    };
+    auto fetch = [&](int i, uint32_t (&dst)[kHN], bool probed = false) {
       const int buf = i & 1;
-      mbar_wait(&bars->s_full[t][buf], (uint32_t)(i >> 1) & 1, err_flag, 301 + t, dead);
+      if (!probed) mbar_wait(&bars->s_full[t][buf], (uint32_t)(i >> 1) & 1, err_flag, 301 + t, dead);
       tc_fence_after();
       tmem_ld32(tS + buf * kHN, &dst[0]);
       tmem_ld32(tS + buf * kHN + 32, &dst[32]);
@@ -671,10 +669,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         raise_max(i, mt_cur);
       }
       uint64_t ls[2] = {0ull, 0ull};
+      bool s_ready = false;
+      if constexpr (kPrefetch) s_ready = probe(i + 1);
       exps(Range<0, kFa>{}, cur, p, kc, ls);
       if (!published) publish(i - 1, p_prev);
       if constexpr (kPrefetch) {
-        fetch(i + 1, nxt);
+        if (tracer) tr[i * 4 + 1] = clock64();
+        fetch(i + 1, nxt, s_ready);
+        if (tracer) tr[i * 4 + 2] = clock64();
         kn = load_consts(i + 1);
         exps(Range<kFa, kFb>{}, cur, p, kc, ls);
         tmem_wait_ld();
@@ -685,7 +687,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         exps(Range<kFa, kHN / 2>{}, cur, p, kc, ls);
       }
       if constexpr (kBlk) fold_sums(ls, kc);
-      if (tracer) tr[i * 4 + 2] = clock64();
     };
     // last step (i == n_half-1): may cover fewer than 64 existing keys; not pipelined
     auto last_step = [&](int i, uint32_t (&cur)[kHN], uint32_t (&p)[kHN / 2], const uint32_t (&p_prev)[kHN / 2]) {
@@ -798,7 +799,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // ---------------------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }

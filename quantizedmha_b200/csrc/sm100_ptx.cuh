@@ -53,6 +53,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// Non-blocking probe of the same condition (never parks the thread).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Same with a suspend-time hint (ns): the hardware may park the thread until the phase completes
 // or the time is up, instead of returning to a software spin loop that burns issue slots.
 __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
@@ -161,6 +173,12 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t c_fmt, uint32_t a_fmt
 //   start address >>4 at [0,14), LBO >>4 at [16,30) (unused for swizzled K-major),
 //   SBO >>4 at [32,46) = 8 rows * row_bytes, version=1 at [46,48), layout type at [61,64):
 //   SWIZZLE_128B = 2, SWIZZLE_64B = 4, SWIZZLE_32B = 6.
+// Descriptor of the same tile `byte_off` bytes further on (multiple of 16; the 14-bit address field
+// must not overflow, i.e. the operand stays inside the 256 KB shared window): one 32-bit add.
+__device__ __forceinline__ uint64_t advance_smem_desc(uint64_t desc, uint32_t byte_off) {
+  const uint32_t lo = (uint32_t)desc + (byte_off >> 4);
+  return (desc & 0xFFFFFFFF00000000ull) | lo;
+}
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t row_bytes) {
   const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
   const uint32_t sbo = 8u * row_bytes;

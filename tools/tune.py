@@ -91,7 +91,7 @@ for kern in ("int8", "f16"):
     if kern == "int8" and d == 128:
         nt = (N + 63) // 64
         for v in (0,):
-            tr = np.zeros((3, nt, 4), np.int64)
+            tr = np.zeros((9, nt, 4), np.int64)
             rc = L.qmha_debug_attention_trace(C.c_void_p(Qp.data_ptr()), C.c_void_p(Kp.data_ptr()), C.c_void_p(Vt.data_ptr()),
                                               C.c_void_p(sc.data_ptr()), C.c_void_p(out.data_ptr()), B, N, dm, H, v,
                                               tr.ctypes.data_as(C.c_void_p))
@@ -99,10 +99,13 @@ for kern in ("int8", "f16"):
                 print("trace failed:", L.qmha_last_error().decode())
                 continue
             np.save(os.path.join(OUT, f"trace_v{v}.npy"), tr)
-            t0 = tr[tr > 0].min()
-            it = np.diff(tr[2, :, 0])
-            print(f"trace v{v}: median MMA iteration {np.median(it):.0f} clk; softmax0 step {np.median(np.diff(tr[0,:,0])):.0f} clk, "
-                  f"start->exp_done {np.median(tr[0,:,2]-tr[0,:,0]):.0f}, publish {np.median(tr[0,:,3]-tr[0,:,2]):.0f}", flush=True)
+            mid = slice(nt // 4, 3 * nt // 4)
+            print(f"trace v{v}: median MMA iteration {np.median(np.diff(tr[8, mid, 0])):.0f} clk", flush=True)
+            for w in range(8):
+                st = np.diff(tr[w, mid, 0])
+                wait = (tr[w, mid, 2] - tr[w, mid, 1])
+                print(f"  softmax warp {w}: step median {np.median(st):.0f} mean {st.mean():.0f} clk; s_full wait mean {wait.mean():.0f} max {wait.max()}; "
+                      f"start->prefetch {np.median(tr[w, mid, 1] - tr[w, mid, 0]):.0f}", flush=True)
     del Qp, Kp, Vt
 os.environ.pop("QMHA_ATTN_VARIANT", None)
 json.dump(res, open(os.path.join(OUT, "tune.json"), "w"), indent=1)
