@@ -327,7 +327,7 @@ __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint3
   }
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 8, int kFb = 24>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, AttnParams prm) {
@@ -526,6 +526,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + (t ? kColS1 : kColS0);
     const uint32_t tO = tmem_base + lane_addr + (t ? kColO1 : kColO0);
+    // measurement aid (QMHA_DEBUG_NO_MMA): P goes to the unused O columns so the score buffers keep sane data
+    const uint32_t tP = prm.debug_no_mma ? tO : tS;
 
     static_assert(!kBlk || kInt8, "block scales only exist for the INT8 variant");
     float c = prm.scale_log2;  // log2(e) / sqrt(d)
@@ -617,7 +619,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // P_t(i) -> TMEM, over the score buffer of step i+1 (its scores are in registers by now),
     // then tell the MMA warp.
     auto publish = [&](int i, const uint32_t (&p)[kHN / 2]) {
-      tmem_st32(tS + ((i + 1) & 1) * kHN, &p[0]);
+      tmem_st32(tP + ((i + 1) & 1) * kHN, &p[0]);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars->p_full[t][i & 1]);
@@ -657,6 +659,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // One pipelined step i < n_half-1 (always unmasked): exponentials of `cur` into `p`; publishes
     // `p_prev` = P(i-1) (if i > 0); if kPrefetch, fetches S(i+1) (unmasked, i.e. i+1 < n_half-1)
     // into `nxt` with row max and vote.
+    using Yes = std::true_type;
+    using No = std::false_type;
+    // One pipelined step i < n_half-1 (always unmasked): exponentials of `cur` into `p`; publishes
+    // `p_prev` = P(i-1) (if i > 0); if kPrefetch, fetches S(i+1) (unmasked, i.e. i+1 < n_half-1)
+    // into `nxt` with row max and vote.
+    // (A separate straight-line "fast path" selected by a vote at the top of the step was measured
+    // slower: the probe -> vote -> branch chain is exposed latency.)
     auto pipe_step = [&](auto prefetch, int i, uint32_t (&cur)[kHN], float mt_cur, bool raise_cur,
                          const StepConsts& kc, uint32_t (&p)[kHN / 2], const uint32_t (&p_prev)[kHN / 2],
                          uint32_t (&nxt)[kHN], float& mt_nxt, bool& raise_nxt, StepConsts& kn) {
@@ -671,20 +680,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint64_t ls[2] = {0ull, 0ull};
       bool s_ready = false;
       if constexpr (kPrefetch) s_ready = probe(i + 1);
+      // Split points (in exp2 pairs) chosen so that this warp never sits on a busy unit: the P store
+      // is issued at kFa and only waited for / signalled three pairs later; the two halves of the score
+      // fetch (TMEM reads run at 64 B/clk: 64 clk per 32-column load) are issued six pairs apart.
+      constexpr int kA1 = kFa + 3, kA2 = kFa + 9;
+      static_assert(kA2 < kFb && kFb < kHN / 2, "split points out of order");
       exps(Range<0, kFa>{}, cur, p, kc, ls);
-      if (!published) publish(i - 1, p_prev);
+      if (!published) tmem_st32(tP + (i & 1) * kHN, &p_prev[0]);  // P(i-1) over the S(i) buffer
+      exps(Range<kFa, kA1>{}, cur, p, kc, ls);
+      if (!published) {
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->p_full[t][(i - 1) & 1]);
+        if (tracer) tr[(i - 1) * 4 + 3] = clock64();
+      }
       if constexpr (kPrefetch) {
         if (tracer) tr[i * 4 + 1] = clock64();
-        fetch(i + 1, nxt, s_ready);
+        const int buf = (i + 1) & 1;
+        if (!s_ready) mbar_wait(&bars->s_full[t][buf], (uint32_t)((i + 1) >> 1) & 1, err_flag, 301 + t, dead);
+        tc_fence_after();
+        tmem_ld32(tS + buf * kHN, &nxt[0]);
         if (tracer) tr[i * 4 + 2] = clock64();
         kn = load_consts(i + 1);
-        exps(Range<kFa, kFb>{}, cur, p, kc, ls);
+        exps(Range<kA1, kA2>{}, cur, p, kc, ls);
+        tmem_ld32(tS + buf * kHN + 32, &nxt[32]);
+        exps(Range<kA2, kFb>{}, cur, p, kc, ls);
         tmem_wait_ld();
         mt_nxt = row_max(nxt, kn, false, kHN);
         raise_nxt = vote_raise(mt_nxt);
         exps(Range<kFb, kHN / 2>{}, cur, p, kc, ls);
       } else {
-        exps(Range<kFa, kHN / 2>{}, cur, p, kc, ls);
+        exps(Range<kA1, kHN / 2>{}, cur, p, kc, ls);
       }
       if constexpr (kBlk) fold_sums(ls, kc);
     };
@@ -717,10 +743,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       publish(i, p);
     };
-    using Yes = std::true_type;
-    using No = std::false_type;
 
     uint32_t sA[kHN], sB[kHN], pA[kHN / 2], pB[kHN / 2];
+    if (prm.debug_no_mma) {
+#pragma unroll
+      for (int q = 0; q < kHN; ++q) sA[q] = (uint32_t)((int)((threadIdx.x * 37 + q * 101) % 4001) - 2000);
+      tmem_st32(tS, &sA[0]); tmem_st32(tS + 32, &sA[32]); tmem_st32(tS + 64, &sA[0]); tmem_st32(tS + 96, &sA[32]);
+      tmem_wait_st();
+    }
     float mtA = 0.f, mtB = 0.f;
     bool raiseA = true, raiseB = true;  // the first step always installs its row max
     StepConsts kA = load_consts(0), kB = kA;
@@ -849,7 +879,7 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
   return true;
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 8, int kFb = 24>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD>;
   const uint64_t units = (uint64_t)a.B * a.H;
