@@ -37,7 +37,7 @@ static bool starts_with(const char* s, const char* p) { return std::strncmp(s, p
 int main(int argc, char** argv) {
   std::string kernel = QMHA_DEFAULT_KERNEL;
   int warmup = 2, runs = 3;
-  bool use_random = false, do_check = true, json = false;
+  bool use_random = false, do_check = true, json = false, rope = false;
   int pN = N, pD = d_model, pH = h, pB = 1;
 
   for (int i = 1; i < argc; ++i) {
@@ -55,9 +55,10 @@ int main(int argc, char** argv) {
     else if (starts_with(a, "--h=")) pH = std::atoi(a + 4);
     else if (starts_with(a, "--B=")) pB = std::atoi(a + 4);
     else if (!std::strcmp(a, "--json")) json = true;
+    else if (!std::strcmp(a, "--rope")) rope = true;  // fused RoPE on Q,K (utils/verify.cu:56-69 semantics)
     else if (!std::strcmp(a, "--help")) {
       std::printf("Usage: %s [--kernel=KERNEL] [--warmup=N] [--runs=M] [--check=0|1] [--no-check] [--random]\n"
-                  "          [--N=rows] [--d_model=cols] [--h=heads] [--B=batch] [--json]\n", argv[0]);
+                  "          [--N=rows] [--d_model=cols] [--h=heads] [--B=batch] [--json] [--rope]\n", argv[0]);
       std::printf("  KERNEL options: fa_tc_int8_b fa_tc_int8_a (INT8 tcgen05 path); fa_tc_v2a fa_tc_v1a fa unfused ...\n"
                   "                  (FP16 tcgen05 path); native names fa_b200_int8, fa_b200_f16\n");
       return 0;
@@ -68,6 +69,10 @@ int main(int argc, char** argv) {
     return 2;
   }
   const int kid = qmha_kernel_from_name(kernel.c_str());
+  if (rope && qmha_set_rope(1, 10000.0f) != 0) {
+    std::fprintf(stderr, "%s\n", qmha_last_error());
+    return 2;
+  }
   mkdir(".cache", 0755);
   const size_t per_batch = (size_t)pN * pD;
 
@@ -102,6 +107,10 @@ int main(int argc, char** argv) {
       for (int r = 0; r < pN; r += std::max(1, pN / 7)) rows.push_back(r);
       rows.push_back(pN - 1);
       std::vector<double> expect;
+      if (rope) {  // the reference's CPU check rotates Q and K (utils/verify.cu:56-69)
+        apply_rope_host(rnd.q, pN, pD, pH);
+        apply_rope_host(rnd.k, pN, pD, pH);
+      }
       expected_rows(rnd.q, rnd.k, rnd.v, pN, pD, pH, rows, expect);
       const float eps = kid == QMHA_KERNEL_INT8 ? 2e-2f : 2e-3f;
       CheckReport rep = compare_rows(got, expect, rows, pD, eps, 1e-3f);

@@ -105,11 +105,23 @@ int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt,
 int qmha_check_async_error(void);
 
 /* Debug/tuning aid: runs the instrumented INT8 d=128 attention kernel once (synchronous) and
- * returns the clock64 timeline of CTA (0,0): host_trace[3][ceil(N/64)][4] (softmax tile 0,
- * softmax tile 1, MMA issuer).  variant k: polynomial exp2 on every k-th pair (0 = none). */
+ * returns the clock64 timeline of CTA (0,0): host_trace[9][ceil(N/64)][4] (softmax warps
+ * 0-7, MMA issuer of tile 0).  variant k: polynomial exp2 on every k-th pair (0 = none). */
 int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* Vt,
                                const float* scales, float* O, int B, int N, int d_model, int h,
                                int variant, long long* host_trace);
+
+/* ---- fused RoPE ------------------------------------------------------------
+ * The reference's CPU check rotates Q and K (utils/verify.cu:56-69) but no GPU kernel ever calls
+ * the device helper apply_rope (utils/utils.cu:50-65).  With qmha_set_rope(1, base) every entry
+ * point (solve, qmha_forward*, qmha_quantize_qkv, qmha_convert_qkv_f16) rotates the Q and K rows
+ * inside the HBM-bound quantise / convert pass, before the block maxima are taken: position =
+ * row index within the batch entry, pairs (k, k + d/2), theta = powf(base, -2k/d) exactly as
+ * verify.cu:9-23 / generate_golden.cpp:38-51.  The rotated values are bit-identical to the CPU
+ * restatement (cos/sin come from a host-built table).  Needs d % 8 == 0 and, for INT8,
+ * QMHA_GRAN_BLOCK.  Process-wide setting; QMHA_ROPE=1 in the environment enables it at start. */
+int qmha_set_rope(int enable, float base);
+int qmha_get_rope(void);
 
 /* ---- housekeeping -------------------------------------------------------------------------- */
 const char* qmha_last_error(void);          /* "" when the last call on this thread succeeded */

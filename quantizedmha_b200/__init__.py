@@ -18,6 +18,7 @@ from .binding import (  # noqa: F401
     flash_solve_ptr,
     forward,
     forward_host,
+    get_rope,
     kernel_id,
     launch_count,
     lib,
@@ -25,6 +26,7 @@ from .binding import (  # noqa: F401
     quantize_blocks,
     quantize_qkv,
     quantize_static,
+    set_rope,
     solve,
     workspace_dims,
 )

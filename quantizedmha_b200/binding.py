@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         L.qmha_get_kernel.restype = C.c_char_p
         L.qmha_kernel_from_name.argtypes = [C.c_char_p]
         L.qmha_default_granularity.argtypes = [i, i]
+        L.qmha_set_rope.argtypes = [i, f]
+        L.qmha_get_rope.argtypes = []
         L.qmha_launch_count.restype = C.c_int64
         L.qmha_version.restype = C.c_char_p
         L.qmha_shutdown.restype = None
@@ -70,6 +72,16 @@ def kernel_id(kernel) -> int:
     if k < 0:
         raise QmhaError(f"unknown kernel {kernel!r}")
     return k
+
+
+def set_rope(enable: bool, base: float = 10000.0) -> None:
+    """Fused RoPE on Q and K inside the quantise / convert pass (utils/verify.cu:9-23 semantics;
+    the reference's CPU check rotates, its GPU kernels never did).  Process-wide."""
+    _check(lib().qmha_set_rope(int(bool(enable)), float(base)))
+
+
+def get_rope() -> bool:
+    return bool(lib().qmha_get_rope())
 
 
 def launch_count() -> int:

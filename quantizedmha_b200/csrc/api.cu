@@ -2,6 +2,7 @@
 // workspaces, error reporting.  Host code only; kernels live in prepare.cu and attn_fwd.cu.
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,10 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::mutex g_mu;
 int g_default_kernel = -2;  // -2 = not resolved yet
+// Fused RoPE on Q and K inside the quantise / convert pass (qmha_set_rope; QMHA_ROPE=1 in the
+// environment turns it on for processes that only call solve(), e.g. bin/profile_* --rope).
+int g_rope = -1;            // -1 = not resolved yet (environment), 0 = off, 1 = on
+float g_rope_base = 10000.0f;
 
 int fail(const std::string& msg) {
   g_err = msg;
@@ -46,6 +51,9 @@ struct Workspace {
   float* vmax = nullptr;   // block mode: [units]
   int* error_flag = nullptr;
   size_t qk_bytes = 0, vt_bytes = 0, scale_elems = 0;
+  float2* rope_tab = nullptr;  // {cos, sin}[rope_n][rope_d/2] for rope_base
+  int rope_n = 0, rope_d = 0;
+  float rope_base = 0.f;
 };
 std::map<int, Workspace> g_ws;  // per device
 
@@ -149,6 +157,43 @@ size_t scale_count(int units, int n_pad, int gran) {
   return gran == QMHA_GRAN_BLOCK ? (size_t)3 * units * (n_pad / 32) : (size_t)3 * units;
 }
 
+bool rope_enabled() {
+  if (g_rope < 0) {
+    const char* env = getenv("QMHA_ROPE");
+    g_rope = (env && *env && *env != '0') ? 1 : 0;
+  }
+  return g_rope == 1;
+}
+
+// {cos, sin} table of the reference's RoPE (utils/verify.cu:9-23: theta = powf(base, -2k/d),
+// angle = pos * theta, sinf / cosf), computed with the host's libm — the same functions the CPU
+// reference calls — so the fused rotation reproduces its fp32 values bit for bit.  Cached per
+// device for the largest N seen with this (d, base).
+int get_rope_table(int dev, int N, int d, float base, const float2** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace& w = g_ws[dev];
+  if (w.rope_tab && w.rope_d == d && w.rope_base == base && w.rope_n >= N) { *out = w.rope_tab; return 0; }
+  const int half = d / 2;
+  std::vector<float2> tab((size_t)N * half);
+  std::vector<float> theta(half);
+  for (int k = 0; k < half; ++k) theta[k] = powf(base, -static_cast<float>(2 * k) / d);
+  for (int pos = 0; pos < N; ++pos)
+    for (int k = 0; k < half; ++k) {
+      const float angle = pos * theta[k];
+      tab[(size_t)pos * half + k] = make_float2(cosf(angle), sinf(angle));
+    }
+  cudaDeviceSynchronize();
+  cudaFree(w.rope_tab);
+  w.rope_tab = nullptr; w.rope_n = 0;
+  cudaError_t e = cudaMalloc(&w.rope_tab, tab.size() * sizeof(float2));
+  if (e != cudaSuccess) return fail_cuda("cudaMalloc(rope table)", e);
+  e = cudaMemcpy(w.rope_tab, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail_cuda("uploading the rope table", e);
+  w.rope_n = N; w.rope_d = d; w.rope_base = base;
+  *out = w.rope_tab;
+  return 0;
+}
+
 int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, int d_model, int h,
                  int kernel, int gran, void* Qp, void* Kp, void* Vt, float* scales, unsigned* amax,
                  cudaStream_t stream) {
@@ -160,6 +205,14 @@ int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, i
   a.B = B; a.N = N; a.H = h; a.d = d; a.n_pad = n_pad; a.d_pad = d_pad;
   a.int8 = kernel == QMHA_KERNEL_INT8;
   a.stream = stream;
+  if (rope_enabled()) {
+    if ((d & 7) != 0) return fail("fused RoPE needs a head dimension that is a multiple of 8");
+    if (a.int8 && gran != QMHA_GRAN_BLOCK)
+      return fail("fused RoPE is implemented for QMHA_GRAN_BLOCK (INT8) and for the F16 kernel");
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (get_rope_table(dev, N, d, g_rope_base, &a.rope)) return 1;
+  }
   cudaError_t e;
   if (a.int8) {
     if (gran == QMHA_GRAN_BLOCK) {
@@ -256,6 +309,15 @@ int qmha_set_kernel(const char* name) {
   g_err.clear();
   return 0;
 }
+
+int qmha_set_rope(int enable, float base) {
+  if (enable && !(base > 1.0f)) return fail("rope base must be > 1");
+  g_rope = enable ? 1 : 0;
+  if (enable) g_rope_base = base;
+  g_err.clear();
+  return 0;
+}
+int qmha_get_rope(void) { return rope_enabled() ? 1 : 0; }
 
 int qmha_default_granularity(int d_model, int h) {
   const char* env = getenv("QMHA_SCALES");
@@ -498,7 +560,7 @@ void qmha_shutdown(void) {
     cudaSetDevice(kv.first);
     Workspace& w = kv.second;
     cudaFree(w.Qp); cudaFree(w.Kp); cudaFree(w.Vt); cudaFree(w.scales); cudaFree(w.amax); cudaFree(w.aux); cudaFree(w.vmax);
-    cudaFree(w.error_flag);
+    cudaFree(w.error_flag); cudaFree(w.rope_tab);
   }
   g_ws.clear();
   cudaSetDevice(cur);

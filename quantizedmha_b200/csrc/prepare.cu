@@ -40,6 +40,48 @@ __device__ __forceinline__ int quant1(float v, float inv_sc) {
   return r < -128 ? -128 : (r > 127 ? 127 : r);
 }
 
+
+// Fused RoPE (next row of SURVEY §8f; reference: utils/verify.cu:9-23 == generate_golden.cpp:38-51
+// == the dead device helper utils/utils.cu:50-65).  Element k of a head row pairs with k + d/2:
+//   row[k]       = x*cos - y*sin          row[k + d/2] = x*sin + y*cos
+// cos/sin come from a host-built table (same libm as the CPU reference, so the rotated fp32 values
+// — and therefore the INT8 codes and scales — stay bit-identical to the CPU restatement); products
+// and sums are rounded separately (__fmul_rn / __fadd_rn: no FMA contraction, as in the scalar
+// CPU loop).  `x` holds columns [4*vec, 4*vec+4) of row n; the partner columns live in another lane
+// of the same row group (rows are spread over kVecPerRow consecutive lanes), fetched by shuffle.
+// Requires d % 8 == 0.  All 32 lanes must call this.
+__device__ __forceinline__ float4 rope_rotate(float4 x, int vec, int n, int N, int d,
+                                              const float2* __restrict__ tab) {
+  const int half_vecs = d >> 3;
+  const bool valid = vec * 4 < d;
+  const bool lo = vec < half_vecs;
+  const int pvec = lo ? vec + half_vecs : vec - half_vecs;
+  const int lane = threadIdx.x & 31;
+  const int src = valid ? lane - vec + pvec : lane;
+  float4 y;
+  y.x = __shfl_sync(0xffffffffu, x.x, src);
+  y.y = __shfl_sync(0xffffffffu, x.y, src);
+  y.z = __shfl_sync(0xffffffffu, x.z, src);
+  y.w = __shfl_sync(0xffffffffu, x.w, src);
+  if (!valid || n >= N) return x;
+  const int kk = (lo ? vec : pvec) * 4;
+  const float4* t = reinterpret_cast<const float4*>(tab + (size_t)n * (d >> 1) + kk);
+  const float4 t0 = __ldg(t), t1 = __ldg(t + 1);  // {cos0, sin0, cos1, sin1}, {cos2, sin2, cos3, sin3}
+  float4 r;
+  if (lo) {  // x = row[k], y = row[k + d/2]
+    r.x = __fsub_rn(__fmul_rn(x.x, t0.x), __fmul_rn(y.x, t0.y));
+    r.y = __fsub_rn(__fmul_rn(x.y, t0.z), __fmul_rn(y.y, t0.w));
+    r.z = __fsub_rn(__fmul_rn(x.z, t1.x), __fmul_rn(y.z, t1.y));
+    r.w = __fsub_rn(__fmul_rn(x.w, t1.z), __fmul_rn(y.w, t1.w));
+  } else {   // y = row[k] (partner), x = row[k + d/2] (mine)
+    r.x = __fadd_rn(__fmul_rn(y.x, t0.y), __fmul_rn(x.x, t0.x));
+    r.y = __fadd_rn(__fmul_rn(y.y, t0.w), __fmul_rn(x.y, t0.z));
+    r.z = __fadd_rn(__fmul_rn(y.z, t1.y), __fmul_rn(x.z, t1.x));
+    r.w = __fadd_rn(__fmul_rn(y.w, t1.w), __fmul_rn(x.w, t1.z));
+  }
+  return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // absmax over [rows r0..r1) of batch b for every head; grid = (row_chunks, B, 3 tensors).
 // amax_bits[z][b*H + head] accumulates max |x| as the bit pattern of a non-negative float
@@ -118,7 +160,8 @@ template <bool kInt8, int kD>
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                const float* __restrict__ V, const float* __restrict__ scales, void* __restrict__ Qp,
-               void* __restrict__ Kp, __half* __restrict__ Vt, int N, int H, int d, int n_pad) {
+               void* __restrict__ Kp, __half* __restrict__ Vt, int N, int H, int d, int n_pad,
+               const float2* __restrict__ rope) {
   const int z = blockIdx.z, unit = blockIdx.y;
   const int b = unit / H, head = unit % H;
   const int n0 = blockIdx.x * kPrepRows;
@@ -154,6 +197,10 @@ prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
       const int n = n0 + r;
       float x[4];
       load4(n, vec * 4, x);
+      if (rope) {  // uniform branch; r covers whole warps, so all lanes take part in the shuffles
+        const float4 rr = rope_rotate(make_float4(x[0], x[1], x[2], x[3]), vec, n, N, d, rope);
+        x[0] = rr.x; x[1] = rr.y; x[2] = rr.z; x[3] = rr.w;
+      }
       const size_t o = ((size_t)unit * n_pad + n) * kD + vec * 4;
       if constexpr (kInt8) {
         const int q0 = quant1(x[0], inv_sc), q1 = quant1(x[1], inv_sc);
@@ -205,7 +252,7 @@ __global__ void __launch_bounds__(kPrepThreads)
 block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                       const float* __restrict__ V, float* __restrict__ scales,
                       int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
-                      int N, int H, int d, int n_pad) {
+                      int N, int H, int d, int n_pad, const float2* __restrict__ rope) {
   const int z = blockIdx.z, unit = blockIdx.y;
   const int b = unit / H, head = unit % H;
   const int n0 = blockIdx.x * kPrepRows;
@@ -226,6 +273,11 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
   for (int k = 0; k < kLoads; ++k) {
     const int n = n0 + rsub + k * kRowsPerIter;
     x[k] = (n < N && col_ok) ? ldg_f4(src + (size_t)n * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (rope && z < 2) {  // rotate Q and K rows before the block maxima are taken (uniform branch)
+#pragma unroll
+    for (int k = 0; k < kLoads; ++k)
+      x[k] = rope_rotate(x[k], vec, n0 + rsub + k * kRowsPerIter, N, d, rope);
   }
   // block maxima: thread -> warp (shuffle) -> CTA (shared memory)
   __shared__ float s_max[kPrepThreads / 32][4];
@@ -294,7 +346,7 @@ cudaError_t launch_block_cfg(const PrepareArgs& a) {
   dim3 grid(a.n_pad / kPrepRows, a.B * a.H, 3);
   block_quantize_kernel<kD><<<grid, kPrepThreads, 0, a.stream>>>(
       a.Q, a.K, a.V, a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
-      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad);
+      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
   return cudaGetLastError();
 }
 
@@ -517,7 +569,8 @@ template <bool kInt8, int kD>
 cudaError_t launch_prepare_cfg(const PrepareArgs& a) {
   dim3 grid(a.n_pad / kPrepRows, a.B * a.H, 3);
   prepare_kernel<kInt8, kD><<<grid, kPrepThreads, 0, a.stream>>>(
-      a.Q, a.K, a.V, a.scales, a.Qp, a.Kp, reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad);
+      a.Q, a.K, a.V, a.scales, a.Qp, a.Kp, reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad,
+      a.rope);
   return cudaGetLastError();
 }
 

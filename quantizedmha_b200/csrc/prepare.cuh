@@ -16,6 +16,9 @@ struct PrepareArgs {
   int B, N, H, d, n_pad, d_pad;
   bool int8;
   cudaStream_t stream;
+  // fused RoPE (utils/verify.cu:9-23 applied to Q and K rows before absmax / quantisation):
+  // table of {cos, sin}(pos * base^(-2k/d)) as float2 [N][d/2], built on the host; nullptr = off
+  const float2* rope = nullptr;
 };
 
 // absmax pass + scale finalisation (3 launches incl. the memset node).

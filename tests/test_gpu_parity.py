@@ -338,3 +338,52 @@ def test_solve_uses_block_scales_by_default(qm, torch, oracle):
     tq, tk, tv = _dev(torch, q, k, v)
     out = qm.solve(tq, tk, tv, 96, 30, 2)
     assert _err(out.cpu().numpy(), oracle.mha(q, k, v, 2, "f64"))[0] <= INT8_MAX_ABS
+
+
+# ---------------------------------------------------------------------------------- fused RoPE
+@pytest.mark.parametrize("shape", [(1, 128, 128, 1), (2, 300, 256, 2), (1, 50, 64, 8), (1, 1024, 256, 4), (1, 200, 192, 2)])
+def test_fused_rope_matches_the_cpu_reference_with_rope(qm, torch, oracle, shape):
+    """RoPE fused into the quantise / convert pass.  The reference's CPU check
+    rotates Q and K (utils/verify.cu:56-69); no reference GPU kernel does.  Here: INT8 codes and
+    block scales of the ROTATED tensors bit-exact vs the CPU restatement (RoPE on the host with the
+    oracle, then the kernel-spec quantiser); attention vs cpu_reference (with RoPE) inside the
+    INT8 / FP16 tolerances; and turning RoPE off restores the plain result."""
+    B, N, dm, h = shape
+    d = dm // h
+    q, k, v = (np.stack([a] * B) for a in oracle.golden_inputs(N, dm, h, rope=False))
+    if B > 1:
+        q[1] *= 1.5
+    qr = np.stack([oracle.apply_rope(x.copy(), h) for x in q])
+    kr = np.stack([oracle.apply_rope(x.copy(), h) for x in k])
+    tq, tk, tv = _dev(torch, q, k, v)
+    assert not qm.get_rope()
+    plain = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_BLOCK).clone()
+    qm.set_rope(True)
+    try:
+        assert qm.get_rope()
+        Qp, Kp, Vt, sc = qm.quantize_qkv(tq, tk, tv, h, qm.GRAN_BLOCK)
+        nb = -(-N // 32)
+        for i, (x, packed, unpack) in enumerate(((qr, Qp, _unpack_rows), (kr, Kp, _unpack_rows), (v, Vt, _unpack_vt))):
+            codes, s = oracle.quantize(x, h, "block", 32)
+            assert np.array_equal(unpack(packed, B, N, h, d), codes.astype(np.float32) if i == 2 else codes), "QKV"[i]
+            assert np.array_equal(sc[i].cpu().numpy()[:, :nb].reshape(-1), s), "QKV"[i]
+        ref = np.stack([oracle.cpu_reference_rope(q[b], k[b], v[b], h) for b in range(B)])
+        out = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_BLOCK)
+        out16 = qm.forward(tq, tk, tv, h, kernel="f16")
+        torch.cuda.synchronize()
+        qm.binding.check_async_error()
+        mx, rel = _err(out.cpu().numpy(), ref)
+        assert mx <= INT8_MAX_ABS and rel <= INT8_REL_L2, (mx, rel)
+        assert _err(out16.cpu().numpy(), ref)[0] <= F16_MAX_ABS
+        # same thing as rotating on the host and running the plain path
+        qm.set_rope(False)
+        host_rot = qm.forward(*_dev(torch, qr, kr, v), h, kernel="int8", gran=qm.GRAN_BLOCK)
+        assert torch.equal(out, host_rot)
+        # unsupported combination fails loudly instead of silently skipping the rotation
+        qm.set_rope(True)
+        with pytest.raises(qm.QmhaError):
+            qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_HEAD)
+    finally:
+        qm.set_rope(False)
+    again = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_BLOCK)
+    assert torch.equal(again, plain)

@@ -40,6 +40,22 @@ void expected_rows(const std::vector<float>& q, const std::vector<float>& k,
   }
 }
 
+void apply_rope_host(std::vector<float>& x, int N, int d_model, int h, float base) {
+  const int d = d_model / h;
+  for (int i = 0; i < N; ++i)
+    for (int head = 0; head < h; ++head) {
+      float* row = &x[(size_t)i * d_model + (size_t)head * d];
+      for (int k = 0; k < d / 2; ++k) {
+        const float theta = std::pow(base, -static_cast<float>(2 * k) / d);
+        const float angle = i * theta;
+        const float sin_a = std::sin(angle), cos_a = std::cos(angle);
+        const float a = row[k], b = row[k + d / 2];
+        row[k] = a * cos_a - b * sin_a;
+        row[k + d / 2] = a * sin_a + b * cos_a;
+      }
+    }
+}
+
 CheckReport compare_rows(const std::vector<float>& out, const std::vector<double>& expect,
                          const std::vector<int>& rows, int d_model, float eps, float rel) {
   CheckReport r;

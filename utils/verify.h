@@ -22,6 +22,10 @@ void expected_rows(const std::vector<float>& q, const std::vector<float>& k,
                    const std::vector<float>& v, int N, int d_model, int h,
                    const std::vector<int>& rows, std::vector<double>& expect);
 
+// RoPE of the reference's CPU check (utils/verify.cu:9-23), applied in place to every head row of a
+// [N, d_model] matrix (position = row index); used by the driver's --rope check.
+void apply_rope_host(std::vector<float>& x, int N, int d_model, int h, float base = 10000.0f);
+
 CheckReport compare_rows(const std::vector<float>& out, const std::vector<double>& expect,
                          const std::vector<int>& rows, int d_model, float eps, float rel);
 
