@@ -36,3 +36,40 @@ def slab_view(x, b: int, h0: int, h1: int, H: int):
     """View of heads [h0,h1) of batch b of a [B, N, H*d] array/tensor -> [N, (h1-h0)*d]."""
     d = x.shape[-1] // H
     return x[b, :, h0 * d:h1 * d]
+
+
+def pack_units(out, B: int, H: int, world: int, rank: int):
+    """This rank's output slabs of a [B, N, H*d] tensor as one contiguous [units_r, N, d] tensor."""
+    import torch
+    d = out.shape[-1] // H
+    parts = [slab_view(out, b, h0, h1, H).reshape(out.shape[1], h1 - h0, d).permute(1, 0, 2)
+             for (b, h0, h1) in shard_slabs(B, H, world, rank)]
+    if not parts:
+        return out.new_zeros((0, out.shape[1], d))
+    return torch.cat(parts, dim=0).contiguous()
+
+
+def gather_outputs(out, B: int, H: int, group=None):
+    """Optional caller-side step, never part of the attention hot path: every rank
+    holds valid data only in its own (batch, head) slabs of `out` [B, N, H*d]; after the call every
+    rank holds the whole tensor.  One all-gather of unit-major [units, N, d] blocks — NCCL over
+    NVLink 5 / NVSwitch for CUDA tensors, gloo for CPU tensors (tests).  Uneven splits are padded to
+    the largest shard."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    N, d = out.shape[1], out.shape[-1] // H
+    counts = [unit_range(B * H, world, r)[1] - unit_range(B * H, world, r)[0] for r in range(world)]
+    cap = max(counts)
+    mine = out.new_zeros((cap, N, d))
+    mine[:counts[rank]] = pack_units(out, B, H, world, rank)
+    bufs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(bufs, mine, group=group)
+    for r in range(world):
+        if r == rank:
+            continue
+        lo, _ = unit_range(B * H, world, r)
+        for j in range(counts[r]):
+            b, h = divmod(lo + j, H)
+            out[b, :, h * d:(h + 1) * d] = bufs[r][j]
+    return out

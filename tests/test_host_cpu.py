@@ -93,7 +93,7 @@ import os, sys
 sys.path.insert(0, {root!r})
 import numpy as np, torch, torch.distributed as dist
 from oracle import load_oracle
-from quantizedmha_b200.sharding import shard_slabs, slab_view
+from quantizedmha_b200.sharding import shard_slabs, slab_view, gather_outputs
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 orc = load_oracle()
@@ -112,6 +112,9 @@ times = torch.tensor([float(rank + 1)])
 dist.all_reduce(times, op=dist.ReduceOp.MAX)
 assert times.item() == float(world)
 assert np.array_equal(t.numpy(), full), "sharded result differs from the unsharded oracle"
+# the optional output gather (SURVEY 8f row 4): every rank ends up with the whole tensor
+g = gather_outputs(torch.from_numpy(mine.copy()), B, H)
+assert np.array_equal(g.numpy(), full), "gathered result differs from the unsharded oracle"
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
