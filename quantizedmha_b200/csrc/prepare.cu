@@ -247,22 +247,27 @@ prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
 // ONE pass: a CTA keeps its 128-row tile (4 blocks) in registers, reduces the four block maxima,
 // then quantises from registers.  HBM traffic = algorithmic (read fp32 once, write codes once).
 //   grid = (n_pad/128, B*H, 3);  scales[z][unit][n_pad/32]
+// kRows = rows per CTA (a multiple of 32): 64 keeps the tile at 8 float4 per thread (<= 64 registers), so four
+// CTAs are resident per SM and the load phase of one overlaps the reduce / store phases of the others
+// (with 128 rows the kernel needs 99 registers, two CTAs per SM, and leaves HBM idle between phases).
+constexpr int kBlkRows = 64;
 template <int kD>
-__global__ void __launch_bounds__(kPrepThreads)
+__global__ void __launch_bounds__(kPrepThreads, 3)
 block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                       const float* __restrict__ V, float* __restrict__ scales,
                       int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
                       int N, int H, int d, int n_pad, const float2* __restrict__ rope) {
-  const int z = blockIdx.z, unit = blockIdx.y;
+  const int z = blockIdx.z, unit = blockIdx.y;  // (heads-fastest CTA order was measured: no gain)
   const int b = unit / H, head = unit % H;
-  const int n0 = blockIdx.x * kPrepRows;
+  const int n0 = blockIdx.x * kBlkRows;
   const float* X = z == 0 ? Q : (z == 1 ? K : V);
   const int d_model = H * d;
   const float* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
 
   constexpr int kVecPerRow = kD / 4;
   constexpr int kRowsPerIter = kPrepThreads / kVecPerRow;  // 8 / 16 / 32 rows per pass
-  constexpr int kLoads = kPrepRows / kRowsPerIter;          // 16 / 8 / 4 float4 per thread
+  constexpr int kLoads = kBlkRows / kRowsPerIter;           // 8 / 4 / 2 float4 per thread
+  constexpr int kBlocks = kBlkRows / 32;                    // 32-row scale blocks per CTA
   constexpr int kPerBlock = 32 / kRowsPerIter;              // loads of one thread per 32-row block
   const int vec = threadIdx.x % kVecPerRow;
   const int rsub = threadIdx.x / kVecPerRow;
@@ -280,10 +285,10 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
       x[k] = rope_rotate(x[k], vec, n0 + rsub + k * kRowsPerIter, N, d, rope);
   }
   // block maxima: thread -> warp (shuffle) -> CTA (shared memory)
-  __shared__ float s_max[kPrepThreads / 32][4];
-  float m[4];
+  __shared__ float s_max[kPrepThreads / 32][kBlocks];
+  float m[kBlocks];
 #pragma unroll
-  for (int blk = 0; blk < 4; ++blk) {
+  for (int blk = 0; blk < kBlocks; ++blk) {
     float v = 0.f;
 #pragma unroll
     for (int k = 0; k < kPerBlock; ++k) v = absmax4(v, x[blk * kPerBlock + k]);
@@ -293,12 +298,12 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
   }
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int blk = 0; blk < 4; ++blk) s_max[threadIdx.x >> 5][blk] = m[blk];
+    for (int blk = 0; blk < kBlocks; ++blk) s_max[threadIdx.x >> 5][blk] = m[blk];
   }
   __syncthreads();
-  float inv_sc[4];
+  float inv_sc[kBlocks];
 #pragma unroll
-  for (int blk = 0; blk < 4; ++blk) {
+  for (int blk = 0; blk < kBlocks; ++blk) {
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < kPrepThreads / 32; ++w) v = fmaxf(v, s_max[w][blk]);
@@ -322,7 +327,7 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
     }
   } else {
     constexpr int kStride = kD + 2;
-    __shared__ __half tile[kPrepRows * kStride];
+    __shared__ __half tile[kBlkRows * kStride];
 #pragma unroll
     for (int k = 0; k < kLoads; ++k) {
       const int r = rsub + k * kRowsPerIter;
@@ -333,8 +338,9 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
       tile[r * kStride + vec * 4 + 3] = __float2half_rn((float)quant1(x[k].w, inv));
     }
     __syncthreads();
-    const int kp = threadIdx.x & 63;
-    for (int dd = threadIdx.x >> 6; dd < kD; dd += kPrepThreads / 64) {
+    constexpr int kPairs = kBlkRows / 2;  // threads per d-row: each emits 2 consecutive keys
+    const int kp = threadIdx.x % kPairs;
+    for (int dd = threadIdx.x / kPairs; dd < kD; dd += kPrepThreads / kPairs) {
       __half2 o2 = __halves2half2(tile[(2 * kp) * kStride + dd], tile[(2 * kp + 1) * kStride + dd]);
       *reinterpret_cast<__half2*>(Vt + ((size_t)unit * kD + dd) * n_pad + n0 + 2 * kp) = o2;
     }
@@ -343,7 +349,7 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
 
 template <int kD>
 cudaError_t launch_block_cfg(const PrepareArgs& a) {
-  dim3 grid(a.n_pad / kPrepRows, a.B * a.H, 3);
+  dim3 grid(a.n_pad / kBlkRows, a.B * a.H, 3);
   block_quantize_kernel<kD><<<grid, kPrepThreads, 0, a.stream>>>(
       a.Q, a.K, a.V, a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
       reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
