@@ -387,3 +387,23 @@ def test_fused_rope_matches_the_cpu_reference_with_rope(qm, torch, oracle, shape
         qm.set_rope(False)
     again = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_BLOCK)
     assert torch.equal(again, plain)
+
+
+# ---------------------------------------------------------------------------------- determinism
+@pytest.mark.parametrize("shape", [(1, 640, 128, 1), (1, 1024, 256, 2), (2, 2048, 512, 4)])
+def test_repeated_runs_are_bit_identical(qm, torch, oracle, shape):
+    """The attention kernel has no atomics and a fixed accumulation order, so repeated launches on
+    the same inputs must agree bit for bit.  This is the regression test for a pipeline hazard
+    (P(i) overwriting P(i-2) before its P·V had retired, only at the tail of sequences with more
+    than ~9 half-steps and only for the warps that run ahead): it showed up as run-to-run
+    differences long before it exceeded any tolerance."""
+    B, N, dm, h = shape
+    q, k, v = (np.stack([a] * B) for a in oracle.golden_inputs(N, dm, h))
+    tq, tk, tv = _dev(torch, q, k, v)
+    for kern, gran in (("int8", qm.GRAN_BLOCK), ("int8", qm.GRAN_HEAD), ("f16", qm.GRAN_HEAD)):
+        first = qm.forward(tq, tk, tv, h, kernel=kern, gran=gran).clone()
+        for _ in range(8):
+            again = qm.forward(tq, tk, tv, h, kernel=kern, gran=gran)
+            torch.cuda.synchronize()
+            assert torch.equal(first, again), (kern, gran)
+    qm.binding.check_async_error()
