@@ -42,13 +42,23 @@ constexpr int kBN = 128;        // keys per KV tile in shared memory (one TMA st
 constexpr int kHN = 64;         // keys per half-step == UMMA N of Q·K^T, UMMA K extent of P·V
 // Service warps 8..11 (one per SM sub-partition).  tcgen05.mma issue visibly slows the softmax
 // warps that share the issuing warp's sub-partition, so the issue work is split: with
+// kMmaSplit == 4 every service warp issues: warp 8+2t+p handles the half-steps of parity p of query
+// tile t, and the TMA production is folded into the even-parity warps (warp 8: Q and the K ring,
+// warp 10: the V^T ring), one tile per iteration, so every sub-partition carries a quarter of the
+// issue work (builds with -DQMHA_MMA_SPLIT=4, passes every GPU test; measured equal to the 2-way split
+// for INT8 — 1397 vs 1404 clk per half-step — so the simpler layout is the default).  With
 // kMmaSplit == 2, warp 8 issues everything for query tile 0 and warp 11 for tile 1 (warps 9 / 10
 // are the K / V TMA producers).
-constexpr int kMmaSplit = 2;
+#ifndef QMHA_MMA_SPLIT
+#define QMHA_MMA_SPLIT 2
+#endif
+constexpr int kMmaSplit = QMHA_MMA_SPLIT;
 constexpr int kAllocWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr int kTmaWarpV = 10;
-__host__ __device__ constexpr bool is_mma_warp(int warp) { return warp == 8 || warp == 11; }
+__host__ __device__ constexpr bool is_mma_warp(int warp) {
+  return kMmaSplit == 4 ? warp >= 8 : (warp == 8 || warp == 11);
+}
 constexpr int kThreads = 384;            // 2 softmax warpgroups + 1 service warpgroup (MMA, TMA, 2 idle)
 constexpr int kRegsSoftmax = 208;        // setmaxnreg budgets: 2*128*208 + 128*72 = 62464 <= 65536
 constexpr int kRegsService = 72;
@@ -387,7 +397,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
    // setmaxnreg sits inside the role branch (which never re-joins the softmax code before the
    // final barrier) so ptxas allocates registers per role.
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsService));
-   if (warp == kTmaWarp) {
+   if (kMmaSplit == 2 && warp == kTmaWarp) {
     // ======================================================================== TMA producer: Q, K ring
     if (lane == 0) {
       const int q_row = unit * prm.n_pad + q_base;
@@ -410,7 +420,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                       sub * (C::kAtomQK / C::kEltQK), k_row0 + j * kBN);
       }
     }
-   } else if (warp == kTmaWarpV) {
+   } else if (kMmaSplit == 2 && warp == kTmaWarpV) {
     // ======================================================================== TMA producer: V^T ring
     if (lane == 0) {
       const int v_row = unit * kD;
@@ -470,16 +480,69 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
       auto commit = [&](uint64_t* bar) { if (leader) mma_commit(bar); };
       const int n_half = prm.n_half_steps;
+      // This warp issues, for query tile `mt`, every half-step i with owns(i).  Half-step i means:
+      // O += P(i)·V(i), then S(i+3) into the score buffer P(i) just left; the scores of half-steps 0..2
+      // belong to the owners of "steps" -3..-1.
+      constexpr int kStride = kMmaSplit == 2 ? 1 : 2;
+      const int mt = kMmaSplit == 2 ? (warp == 8 ? 0 : 1) : ((warp - 8) >> 1);
+      const int first = kMmaSplit == 2 ? 0 : ((warp - 8) & 1);
+      auto owns = [&](int step) { return kStride == 1 || (step & 1) == first; };
+
+      // ---- folded TMA production (kMmaSplit == 4): warp 8 = Q + K ring, warp 10 = V^T ring
+      const bool k_prod = kMmaSplit == 4 && warp == 8, v_prod = kMmaSplit == 4 && warp == 10;
+      auto load_k = [&](int j) {   // K tile j -> stage j % kStagesK (the stage must be free)
+        const int st = j % C::kStagesK;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->k_full[st], C::kTileBytesQK);
+#pragma unroll
+          for (int sub = 0; sub < C::kSubQK; ++sub)
+            tma_load_2d(sK + st * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_k, &bars->k_full[st],
+                        sub * (C::kAtomQK / C::kEltQK), unit * prm.n_pad + j * kBN);
+        }
+      };
+      auto load_v = [&](int j) {
+        const int st = j % C::kStagesV;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->v_full[st], C::kTileBytesV);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+            tma_load_2d(sV + st * C::kTileBytesV + sub * C::kSubBytesV, &tm_v, &bars->v_full[st],
+                        j * kBN + sub * 64, unit * kD);
+        }
+      };
+      if (k_prod) {
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->q_full, 2 * C::kTileBytesQK);
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int sub = 0; sub < C::kSubQK; ++sub)
+              tma_load_2d(sQ + t * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_q, &bars->q_full,
+                          sub * (C::kAtomQK / C::kEltQK), unit * prm.n_pad + q_base + t * kBM);
+        }
+        for (int j = 0; j < C::kStagesK && j < n_tiles; ++j) load_k(j);
+      }
+      if (v_prod)
+        for (int j = 0; j < C::kStagesV && j < n_tiles; ++j) load_v(j);
+      // At the top of the iteration that handles tile j (even parity, j >= 1): tile j-1 was last read one
+      // or two half-steps ago by every issuing warp; once its stage is free, tile j-1+stages goes in.
+      auto refill = [&](int j) {
+        if (j < 1) return;
+        if (k_prod && j - 1 + C::kStagesK < n_tiles) {
+          const int x = j - 1;
+          mbar_wait(&bars->k_empty[x % C::kStagesK], (uint32_t)(x / C::kStagesK) & 1, err_flag, 101, dead);
+          load_k(x + C::kStagesK);
+        }
+        if (v_prod && j - 1 + C::kStagesV < n_tiles) {
+          const int x = j - 1;
+          mbar_wait(&bars->v_empty[x % C::kStagesV], (uint32_t)(x / C::kStagesV) & 1, err_flag, 102, dead);
+          load_v(x + C::kStagesV);
+        }
+      };
+
       mbar_wait(&bars->q_full, 0, err_flag, 201, dead);
       tc_fence_after();
       __syncwarp();
-      // This warp issues, for query tile `mt`, every half-step i with owns(i) — all of them when the
-      // work is split by tile only.  Half-step i means: O += P(i)·V(i), then S(i+3) into the score
-      // buffer P(i) just left; the scores of half-steps 0..2 belong to the owners of "steps" -3..-1.
-      const int mt = warp == 8 ? 0 : 1;
-      constexpr int kStride = kMmaSplit == 2 ? 1 : 2;
-      const int first = 0;
-      auto owns = [&](int step) { return kStride == 1 || (step & 1) == first; };
       auto qk_step = [&](int in, int wait_site) {   // S_mt(in): wait for its K tile, issue, signal, release
         const int jn = in >> 1, halfn = in & 1, stn = jn % C::kStagesK;
         mbar_wait(&bars->k_full[stn], (uint32_t)(jn / C::kStagesK) & 1, err_flag, wait_site, dead);
@@ -502,6 +565,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int st = j % C::kStagesV;
         long long* trm = kTrace ? prm.trace + (size_t)8 * n_half * 4 + (size_t)i * 4 : nullptr;
         const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && mt == 0;
+        if constexpr (kMmaSplit == 4) refill(j);   // only warps 8 / 10 do anything here (even i)
         mbar_wait(&bars->v_full[st], (uint32_t)(j / C::kStagesV) & 1, err_flag, 203, dead);
         mbar_wait(&bars->p_full[mt][half], (uint32_t)(i >> 1) & 1, err_flag, 204, dead);
         if (kStride == 2 && i > 0)  // the other warp's P·V(i-1) must have retired before O is touched again
