@@ -1,5 +1,7 @@
-// jax_ext.cpp — same pointer ABI as the reference's extensions/jax/jax_ext.cpp:12-36: device
-// addresses as integers, forwarded to the C entry point.  No JAX/CuPy needed to build or test it.
+// jax_ext.cpp — Python module `jax_ext`: the raw-pointer ABI of the reference's
+// extensions/jax/jax_ext.cpp:12-36.  The caller (JAX via DLPack/CuPy, or anything else that can
+// produce device addresses) passes four integers and the shape; nothing here depends on JAX, CuPy
+// or PyTorch, so the module builds and is tested with plain pybind11.
 #include <pybind11/pybind11.h>
 
 #include <cstdint>
@@ -8,21 +10,31 @@
 
 #include "../../include/launchers.h"
 
-namespace py = pybind11;
+namespace {
 
-void flash_solve(unsigned long long q_ptr, unsigned long long k_ptr, unsigned long long v_ptr,
-                 unsigned long long out_ptr, int N, int d_model, int num_heads,
-                 const std::string& kernel = "fa_tc_int8_b") {
-  if (qmha_set_kernel(kernel.c_str()) != 0) throw std::invalid_argument(qmha_last_error());
-  solve(reinterpret_cast<const float*>(q_ptr), reinterpret_cast<const float*>(k_ptr),
-        reinterpret_cast<const float*>(v_ptr), reinterpret_cast<float*>(out_ptr), N, d_model,
-        num_heads);  // synchronous on return, like the reference
-  if (*qmha_last_error()) throw std::runtime_error(qmha_last_error());
+template <typename T>
+T* device_ptr(std::uintptr_t address) {
+  return reinterpret_cast<T*>(address);
 }
 
+// Synchronous on return, like the reference's `solve`; errors become Python exceptions instead of
+// being dropped (the reference ignores CUDA errors inside launch(), include/launchers.h:27-71).
+void run(std::uintptr_t q, std::uintptr_t k, std::uintptr_t v, std::uintptr_t out, int rows,
+         int width, int heads, const std::string& variant) {
+  if (qmha_set_kernel(variant.c_str()) != 0) throw std::invalid_argument(qmha_last_error());
+  solve(device_ptr<const float>(q), device_ptr<const float>(k), device_ptr<const float>(v),
+        device_ptr<float>(out), rows, width, heads);
+  const char* problem = qmha_last_error();
+  if (problem && problem[0] != '\0') throw std::runtime_error(problem);
+}
+
+}  // namespace
+
 PYBIND11_MODULE(jax_ext, m) {
-  m.doc() = "Pointer-based wrapper of the B200 quantised-MHA `solve` (JAX / DLPack / CuPy callers)";
-  m.def("flash_solve", &flash_solve, "Call `solve` with device pointers (uint64 addresses)",
-        py::arg("q_ptr"), py::arg("k_ptr"), py::arg("v_ptr"), py::arg("out_ptr"), py::arg("N"),
-        py::arg("d_model"), py::arg("num_heads"), py::arg("kernel") = "fa_tc_int8_b");
+  namespace py = pybind11;
+  m.doc() = "B200 quantised multi-head attention: `solve` on raw device addresses";
+  m.def("flash_solve", &run, py::arg("q_ptr"), py::arg("k_ptr"), py::arg("v_ptr"), py::arg("out_ptr"),
+        py::arg("N"), py::arg("d_model"), py::arg("num_heads"), py::arg("kernel") = "fa_tc_int8_b",
+        "flash_solve(q_ptr, k_ptr, v_ptr, out_ptr, N, d_model, num_heads, kernel): attention forward on\n"
+        "fp32 device buffers [N, d_model] given as integer addresses; returns when the result is complete.");
 }

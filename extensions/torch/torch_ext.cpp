@@ -1,47 +1,60 @@
-// torch_ext.cpp — same Python surface as the reference's extensions/torch/torch_ext.cpp:11-57
-// (module `torch_ext`, flash_solve(Q, K, V, d_model, num_heads, kernel="fa_tc_int8_b")), bound
-// to the B200 library's stream-ordered C entry point.  PyTorch appears only here: tensors in,
-// raw pointers + the current CUDA stream out.
+// torch_ext.cpp — Python module `torch_ext` with the reference's entry point
+//   flash_solve(Q, K, V, d_model, num_heads, kernel="fa_tc_int8_b") -> Tensor
+// (surface of extensions/torch/torch_ext.cpp:11-57 in the reference), implemented on the B200
+// library's stream-ordered C-ABI.  PyTorch appears only here: tensors in, raw pointers and torch's
+// current CUDA stream out.  Differences from the reference wrapper: `kernel` really selects the
+// variant, a leading batch dimension is accepted, the work is enqueued on the caller's stream.
 #include <ATen/cuda/CUDAContext.h>
 #include <torch/extension.h>
 
+#include <array>
 #include <string>
 
 #include "../../include/launchers.h"
 
-using torch::Tensor;
-namespace py = pybind11;
+namespace {
 
-Tensor flash_solve(const Tensor& Q, const Tensor& K, const Tensor& V, int64_t d_model,
-                   int64_t num_heads, const std::string& kernel = "fa_tc_int8_b") {
-  TORCH_CHECK(Q.is_cuda() && K.is_cuda() && V.is_cuda(), "Inputs must be CUDA tensors");
-  TORCH_CHECK(Q.dtype() == torch::kFloat32, "Q must be float32");
-  TORCH_CHECK(K.dtype() == torch::kFloat32, "K must be float32");
-  TORCH_CHECK(V.dtype() == torch::kFloat32, "V must be float32");
-  TORCH_CHECK(Q.sizes() == K.sizes() && Q.sizes() == V.sizes(), "Q, K, V must have the same shape");
-  auto Qc = Q.contiguous(), Kc = K.contiguous(), Vc = V.contiguous();
-  const int64_t elems = Qc.numel();
-  TORCH_CHECK(elems % d_model == 0, "Q.numel() must be divisible by d_model");
-  // [N, d_model] like the reference, or [B, N, d_model]
-  const int64_t B = Qc.dim() == 3 ? Qc.size(0) : 1;
-  const int64_t N = elems / d_model / B;
-  auto out = torch::empty_like(Qc);
-  const int kid = qmha_kernel_from_name(kernel.c_str());
-  TORCH_CHECK(kid >= 0, "unknown kernel '", kernel, "'");
-  const int rc = qmha_forward(Qc.data_ptr<float>(), Kc.data_ptr<float>(), Vc.data_ptr<float>(),
-                              out.data_ptr<float>(), (int)B, (int)N, (int)d_model, (int)num_heads, kid,
-                              qmha_default_granularity((int)d_model, (int)num_heads),
-                              at::cuda::getCurrentCUDAStream().stream());
-  TORCH_CHECK(rc == 0, qmha_last_error());
-  return out;
+struct Problem {
+  int batch, rows, width, heads;
+};
+
+// Validates the three operands the way the reference does (CUDA, float32) and derives the shape.
+Problem describe(const std::array<const at::Tensor*, 3>& qkv, int64_t d_model, int64_t num_heads) {
+  static const char* const names[3] = {"Q", "K", "V"};
+  for (const at::Tensor* t : qkv) TORCH_CHECK(t->is_cuda(), "Inputs must be CUDA tensors");
+  for (int i = 0; i < 3; ++i)
+    TORCH_CHECK(qkv[i]->scalar_type() == at::kFloat, names[i], " must be float32");
+  for (int i = 1; i < 3; ++i)
+    TORCH_CHECK(qkv[i]->sizes() == qkv[0]->sizes(), "Q, K, V must have the same shape");
+  const at::Tensor& q = *qkv[0];
+  TORCH_CHECK(d_model > 0 && q.numel() % d_model == 0, "Q.numel() must be divisible by d_model");
+  const int64_t batch = q.dim() == 3 ? q.size(0) : 1;  // [B, N, d_model] or the reference's [N, d_model]
+  return {(int)batch, (int)(q.numel() / d_model / batch), (int)d_model, (int)num_heads};
 }
 
+at::Tensor flash_solve(const at::Tensor& Q, const at::Tensor& K, const at::Tensor& V,
+                       int64_t d_model, int64_t num_heads, const std::string& kernel) {
+  const Problem p = describe({&Q, &K, &V}, d_model, num_heads);
+  const int variant = qmha_kernel_from_name(kernel.c_str());
+  TORCH_CHECK(variant >= 0, "unknown kernel '", kernel, "'");
+  const at::Tensor q = Q.contiguous(), k = K.contiguous(), v = V.contiguous();
+  at::Tensor result = at::empty_like(q);
+  const int status = qmha_forward(q.data_ptr<float>(), k.data_ptr<float>(), v.data_ptr<float>(),
+                                  result.data_ptr<float>(), p.batch, p.rows, p.width, p.heads, variant,
+                                  qmha_default_granularity(p.width, p.heads),
+                                  at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(status == 0, qmha_last_error());
+  return result;
+}
+
+}  // namespace
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-  m.def("flash_solve", &flash_solve,
-        "Fused multi-head attention forward on B200 (tcgen05).\n\n"
-        "Args:\n  Q, K, V: float32 CUDA tensors [N, d_model] or [B, N, d_model]\n"
-        "  d_model: model dimension\n  num_heads: attention heads (d_model/num_heads <= 128)\n"
-        "  kernel: 'fa_tc_int8_b' (INT8, default), 'fa_tc_v2a' (FP16) or any reference kernel name",
-        py::arg("Q"), py::arg("K"), py::arg("V"), py::arg("d_model"), py::arg("num_heads"),
-        py::arg("kernel") = "fa_tc_int8_b");
+  namespace py = pybind11;
+  m.def("flash_solve", &flash_solve, py::arg("Q"), py::arg("K"), py::arg("V"), py::arg("d_model"),
+        py::arg("num_heads"), py::arg("kernel") = "fa_tc_int8_b",
+        "Multi-head attention forward on a B200 (tcgen05 kernels behind the `solve` C-ABI).\n"
+        "Q, K, V: float32 CUDA tensors, [N, d_model] or [B, N, d_model]; d_model / num_heads <= 128.\n"
+        "kernel: any reference kernel name — the INT8 family (fa_tc_int8_a/b) or the FP16 family\n"
+        "(fa, unfused, fa_tc_v1a ... fa_tc_v2b) — or the native names fa_b200_int8 / fa_b200_f16.");
 }
