@@ -431,7 +431,8 @@ int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B
 }
 
 // Debug: runs the traced INT8 d=128 kernel once (synchronously) and copies the timeline of CTA
-// (0,0) to host_trace[9][ceil(N/64)][4] (clock64 stamps: softmax warps 0-7, MMA warp).
+// in the middle of the grid to host_trace[9][ceil(N/64)][4] (clock64 stamps: softmax warps 0-7, MMA
+// warp) followed by 8 phase stamps of the CTA (entry, setup, first scores, last P, O final, stores, exit).
 int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* Vt,
                                const float* scales, float* O, int B, int N, int d_model, int h,
                                int variant, long long* host_trace) {
@@ -439,7 +440,7 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
   if (dev < 0) return 1;
   Workspace* w;
   if (get_workspace(dev, 0, 0, 0, &w)) return 1;
-  const size_t n = (size_t)9 * ((N + 63) / 64) * 4;
+  const size_t n = (size_t)9 * ((N + 63) / 64) * 4 + 8;
   long long* dtrace = nullptr;
   cudaError_t e = cudaMalloc(&dtrace, n * sizeof(long long));
   if (e != cudaSuccess) return fail_cuda("cudaMalloc(trace)", e);

@@ -361,6 +361,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   bool dead = false;
 
   if (*((volatile int*)err_flag) != 0) return;  // an earlier CTA already failed: drain the grid
+  // traced build: a CTA from the middle of the run (steady state, warm caches); phase stamps of its
+  // warp 0 go behind the per-step stamps: entry, setup done, first scores, last P, O final, stores, exit
+  const bool traced_cta = kTrace && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2;
+  long long* phase = kTrace ? prm.trace + (size_t)9 * prm.n_half_steps * 4 : nullptr;
+  if (traced_cta && threadIdx.x == 0) phase[0] = clock64();
 
   if (warp == kTmaWarp && lane == 0) {
     prefetch_tmap(&tm_q);
@@ -564,7 +569,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int j = i >> 1, half = i & 1;
         const int st = j % C::kStagesV;
         long long* trm = kTrace ? prm.trace + (size_t)8 * n_half * 4 + (size_t)i * 4 : nullptr;
-        const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && mt == 0;
+        const bool tracer = traced_cta && lane == 0 && mt == 0;
         if constexpr (kMmaSplit == 4) refill(j);   // only warps 8 / 10 do anything here (even i)
         mbar_wait(&bars->v_full[st], (uint32_t)(j / C::kStagesV) & 1, err_flag, 203, dead);
         mbar_wait(&bars->p_full[mt][half], (uint32_t)(i >> 1) & 1, err_flag, 204, dead);
@@ -615,8 +620,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int n_half = prm.n_half_steps;
     // trace layout: [8 softmax warps + MMA][n_half][4]; softmax: step start, before / after the
     // s_full wait of the prefetch, P(i) published
-    const bool tracer = kTrace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+    const bool tracer = traced_cta && lane == 0;
     long long* tr = kTrace ? prm.trace + (size_t)warp * n_half * 4 : nullptr;
+    if (tracer && warp == 0) phase[1] = clock64();
 
     // block mode: per-32-key-block constants {sK, log2 r, 1/r, -} of this unit staged in shared memory
     // once per CTA (256 softmax threads), so the per-step lookups are two broadcast LDS.128.
@@ -825,6 +831,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&bars->s0_read[t]);  // buffer 0 is free for S(2)
+      if (tracer && warp == 0) phase[2] = clock64();
       mtA = row_max(sA, kA, false, kHN);
       bool in_a = true;
       while (i + 2 < n_half) {
@@ -848,11 +855,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       last_step(0, sA, pA, pB);
     }
 
+    if (tracer && warp == 0) phase[3] = clock64();
     // ---------------------------------------------------------------- epilogue: O * sV / l
     // (a parity wait on pv_done could alias here: the barrier may be two phases behind)
     mbar_wait(&bars->o_final[t], 0, err_flag, 321 + t, dead);
     dead = __any_sync(0xffffffffu, dead);
     tc_fence_after();
+    if (tracer && warp == 0) phase[4] = clock64();
     float l, la, lb, lc, ld;
     unpack2(lsum[0], la, lb);
     unpack2(lsum[1], lc, ld);
@@ -863,27 +872,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float* out = prm.O + ((size_t)b * prm.N + row) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d;
     const bool row_ok = row < prm.N;
     const bool vec_ok = (prm.d & 3) == 0;
+    // Each thread owns one output row, so direct stores touch 32 different rows per instruction
+    // (16 B each): measured 9.5 k clk per CTA, 5 % of its life.  When the Q tile of this warpgroup is
+    // large enough (>= 16 KB; it is dead by now: every Q·K^T of the tile has retired) the rows of a warp
+    // are staged through it, 32 columns at a time, XOR-swizzled in 16-byte units, and written out as
+    // whole 128-byte row segments (8 lanes per row, 4 rows per instruction).
+    constexpr bool kStaged = C::kTileBytesQK >= 16384;
+    if (kStaged && vec_ok) {
+      float* stage = reinterpret_cast<float*>(sQ + t * C::kTileBytesQK) + (warp & 3) * 1024;  // 32 x 32 floats
+      const int r_sub = lane >> 3, c4 = lane & 7;
+      const int row0 = q_base + t * kBM + (warp & 3) * 32;          // first row of this warp
+      float* out0 = prm.O + ((size_t)b * prm.N + row0) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d;
 #pragma unroll
-    for (int ch = 0; ch < kD / 32; ++ch) {
-      uint32_t o[32];
-      tmem_ld32(tO + ch * 32, o);
-      tmem_wait_ld();
-      if (row_ok) {
-        if (vec_ok) {
+      for (int ch = 0; ch < kD / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tO + ch * 32, o);
+        tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int col = ch * 32 + i;
-            if (col < prm.d) {
-              float4 v = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
-                                     __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-              *reinterpret_cast<float4*>(out + col) = v;
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
+                                       __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+        }
+        __syncwarp();
+        const int col = ch * 32 + c4 * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + r_sub;
+          const float4 v = *reinterpret_cast<const float4*>(stage + r * 32 + ((c4 ^ (r & 7)) << 2));
+          if (row0 + r < prm.N && col < prm.d)
+            *reinterpret_cast<float4*>(out0 + (size_t)r * ((size_t)prm.H * prm.d) + col) = v;
+        }
+        __syncwarp();
+      }
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < kD / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tO + ch * 32, o);
+        tmem_wait_ld();
+        if (row_ok) {
+          if (vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const int col = ch * 32 + i;
+              if (col < prm.d) {
+                float4 v = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
+                                       __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                *reinterpret_cast<float4*>(out + col) = v;
+              }
             }
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = ch * 32 + i;
-            if (col < prm.d) out[col] = __uint_as_float(o[i]) * inv;
+            for (int i = 0; i < 32; ++i) {
+              const int col = ch * 32 + i;
+              if (col < prm.d) out[col] = __uint_as_float(o[i]) * inv;
+            }
           }
         }
       }
@@ -891,8 +935,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 
   // ---------------------------------------------------------------------------- teardown
+  if (traced_cta && threadIdx.x == 0) phase[5] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (traced_cta && threadIdx.x == 0) phase[6] = clock64();
   if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

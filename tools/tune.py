@@ -91,14 +91,18 @@ for kern in ("int8", "f16"):
     if kern == "int8" and d == 128:
         nt = (N + 63) // 64
         for v in (0,):
-            tr = np.zeros((9, nt, 4), np.int64)
+            buf = np.zeros(9 * nt * 4 + 8, np.int64)
             rc = L.qmha_debug_attention_trace(C.c_void_p(Qp.data_ptr()), C.c_void_p(Kp.data_ptr()), C.c_void_p(Vt.data_ptr()),
                                               C.c_void_p(sc.data_ptr()), C.c_void_p(out.data_ptr()), B, N, dm, H, v,
-                                              tr.ctypes.data_as(C.c_void_p))
+                                              buf.ctypes.data_as(C.c_void_p))
             if rc != 0:
                 print("trace failed:", L.qmha_last_error().decode())
                 continue
+            tr = buf[:9 * nt * 4].reshape(9, nt, 4)
+            ph = buf[9 * nt * 4:]
             np.save(os.path.join(OUT, f"trace_v{v}.npy"), tr)
+            print("CTA phases (clk): setup %d, to first scores %d, main loop %d, wait O final %d, stores %d, exit barrier %d; total %d" % (
+                ph[1] - ph[0], ph[2] - ph[1], ph[3] - ph[2], ph[4] - ph[3], ph[5] - ph[4], ph[6] - ph[5], ph[6] - ph[0]), flush=True)
             mid = slice(nt // 4, 3 * nt // 4)
             print(f"trace v{v}: median MMA iteration {np.median(np.diff(tr[8, mid, 0])):.0f} clk", flush=True)
             for w in range(8):
