@@ -440,7 +440,7 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
   if (dev < 0) return 1;
   Workspace* w;
   if (get_workspace(dev, 0, 0, 0, &w)) return 1;
-  const size_t n = (size_t)9 * ((N + 63) / 64) * 4 + 8;
+  const size_t n = (size_t)9 * ((N + 63) / 64) * 4 + 16;
   long long* dtrace = nullptr;
   cudaError_t e = cudaMalloc(&dtrace, n * sizeof(long long));
   if (e != cudaSuccess) return fail_cuda("cudaMalloc(trace)", e);

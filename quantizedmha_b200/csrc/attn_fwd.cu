@@ -27,6 +27,7 @@
 //                          O0 = [256,384)  O1 = [384,512);  S_t(j) lives in S_t[j&1], P_t(i) in the
 //                          first 32 columns of S_t[(i+1)&1].
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include "attn_fwd.cuh"
 #include "sm100_ptx.cuh"
@@ -107,6 +108,7 @@ struct Barriers {
   uint64_t s_full[2][2], p_full[2][2], pv_done[2][2];  // [tile][buffer / step parity]
   uint64_t o_final[2];                              // one-shot: last P·V of the tile retired
   uint64_t s0_read[2];                              // one-shot: S_t(0) copied to registers
+  uint64_t qk_done;                                 // one-shot: every Q·K^T of the CTA retired (K ring is free)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -340,7 +342,8 @@ __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint3
 template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, AttnParams prm) {
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+                AttnParams prm) {
   using C = Cfg<kInt8, kD>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles.
@@ -387,7 +390,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&bars->o_final[t], 1);
       mbar_init(&bars->s0_read[t], 128);
     }
+    mbar_init(&bars->qk_done, kMmaSplit);
     fence_mbar_init();
+    if constexpr (kMmaSplit == 2) {
+      // Q and the first K tiles are requested right here, before the CTA-wide barrier: the TMEM
+      // allocation and the barrier itself then overlap the ~1.5 k clk of TMA latency.
+      mbar_arrive_expect_tx(&bars->q_full, 2 * C::kTileBytesQK);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int sub = 0; sub < C::kSubQK; ++sub)
+          tma_load_2d(sQ + t * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_q, &bars->q_full,
+                      sub * (C::kAtomQK / C::kEltQK), unit * prm.n_pad + q_base + t * kBM);
+      for (int j = 0; j < C::kStagesK && j < n_tiles; ++j) {
+        mbar_arrive_expect_tx(&bars->k_full[j], C::kTileBytesQK);
+#pragma unroll
+        for (int sub = 0; sub < C::kSubQK; ++sub)
+          tma_load_2d(sK + j * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_k, &bars->k_full[j],
+                      sub * (C::kAtomQK / C::kEltQK), unit * prm.n_pad + j * kBN);
+      }
+    }
   }
   if (warp == kAllocWarp) {
     tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -404,17 +426,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsService));
    if (kMmaSplit == 2 && warp == kTmaWarp) {
     // ======================================================================== TMA producer: Q, K ring
-    if (lane == 0) {
-      const int q_row = unit * prm.n_pad + q_base;
-      mbar_arrive_expect_tx(&bars->q_full, 2 * C::kTileBytesQK);
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int sub = 0; sub < C::kSubQK; ++sub)
-          tma_load_2d(sQ + t * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_q, &bars->q_full,
-                      sub * (C::kAtomQK / C::kEltQK), q_row + t * kBM);
+    if (lane == 0) {  // Q and K tiles 0 .. kStagesK-1 were requested during the CTA setup
       const int k_row0 = unit * prm.n_pad;
-      for (int j = 0; j < n_tiles; ++j) {
+      for (int j = C::kStagesK; j < n_tiles; ++j) {
         const int st = j % C::kStagesK;
         const uint32_t ph = (uint32_t)(j / C::kStagesK);
         if (j >= C::kStagesK) mbar_wait(&bars->k_empty[st], (ph - 1) & 1, err_flag, 101, dead);
@@ -565,6 +579,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         qk_step(in, 202);
       }
+      if (first + 3 >= n_half) commit(&bars->qk_done);  // this warp issues no further Q·K^T
       for (int i = first; i < n_half; i += kStride) {
         const int j = i >> 1, half = i & 1;
         const int st = j % C::kStagesV;
@@ -582,7 +597,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (i == n_half - 1) commit(&bars->o_final[mt]);
         if (kStride == 2 || half == 1 || i == n_half - 1) commit(&bars->v_empty[st]);
         if (tracer) trm[1] = clock64();
-        if (i + 3 < n_half) qk_step(i + 3, 205);
+        if (i + 3 < n_half) {
+          qk_step(i + 3, 205);
+          if (i + 3 + kStride >= n_half) commit(&bars->qk_done);  // that was this warp's last Q·K^T
+        }
         if (tracer) trm[3] = clock64();
       }
     }
@@ -857,11 +875,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     if (tracer && warp == 0) phase[3] = clock64();
     // ---------------------------------------------------------------- epilogue: O * sV / l
-    // (a parity wait on pv_done could alias here: the barrier may be two phases behind)
-    mbar_wait(&bars->o_final[t], 0, err_flag, 321 + t, dead);
-    dead = __any_sync(0xffffffffu, dead);
-    tc_fence_after();
-    if (tracer && warp == 0) phase[4] = clock64();
+    // Everything that does not need O is computed before the wait (the divisions alone are ~300 clk).
     float l, la, lb, lc, ld;
     unpack2(lsum[0], la, lb);
     unpack2(lsum[1], lc, ld);
@@ -872,26 +886,79 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float* out = prm.O + ((size_t)b * prm.N + row) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d;
     const bool row_ok = row < prm.N;
     const bool vec_ok = (prm.d & 3) == 0;
-    // Each thread owns one output row, so direct stores touch 32 different rows per instruction
-    // (16 B each): measured 9.5 k clk per CTA, 5 % of its life.  When the Q tile of this warpgroup is
-    // large enough (>= 16 KB; it is dead by now: every Q·K^T of the tile has retired) the rows of a warp
-    // are staged through it, 32 columns at a time, XOR-swizzled in 16-byte units, and written out as
-    // whole 128-byte row segments (8 lanes per row, 4 rows per instruction).
     constexpr bool kStaged = C::kTileBytesQK >= 16384;
-    if (kStaged && vec_ok) {
+    constexpr bool kTmaStore = C::kStagesK * C::kTileBytesQK >= 65536;
+    // (a parity wait on pv_done could alias here: the barrier may be two phases behind)
+    mbar_wait(&bars->o_final[t], 0, err_flag, 321 + t, dead);
+    dead = __any_sync(0xffffffffu, dead);
+    tc_fence_after();
+    if (tracer && warp == 0) phase[4] = clock64();
+    // Each thread owns one output row, so direct stores touch 32 different rows per instruction
+    // (16 B each): measured 9.5 k clk per CTA, 5 % of its life.  Best case: the whole K ring is free
+    // (every Q·K^T of both tiles has retired), it is at least 64 KB and d is a multiple of 32: each warp
+    // stages 32 rows x 32 columns per 128B-swizzled 4 KB tile of the ring (two tiles per warp) and one
+    // lane hands them to the TMA as tensor stores; rows beyond N are clipped by the tensor map
+    // ([B][N][H*d], box 1 x 32 x 32).  All TMEM loads are issued up front, one proxy fence per two tiles.
+    if (kTmaStore && prm.tma_store) {
+      mbar_wait(&bars->qk_done, 0, err_flag, 341 + t, dead);
+      float* stage = reinterpret_cast<float*>(sK) + warp * 2048;   // 2 x (32 rows x 32 floats) per warp
+      const int row0 = q_base + t * kBM + (warp & 3) * 32;
+      constexpr int kChunks = kD / 32;
+      uint32_t o[kChunks][32];
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) tmem_ld32(tO + ch * 32, o[ch]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int rnd = 0; rnd < (kChunks + 1) / 2; ++rnd) {
+        if (rnd > 0) {
+          if (lane == 0) bulk_wait_group_read<0>();  // the previous round's stores have read both tiles
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int ch = rnd * 2 + c;
+          if (ch < kChunks) {
+            float* buf = stage + c * 1024;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 v = make_float4(__uint_as_float(o[ch][4 * j]) * inv, __uint_as_float(o[ch][4 * j + 1]) * inv,
+                                           __uint_as_float(o[ch][4 * j + 2]) * inv, __uint_as_float(o[ch][4 * j + 3]) * inv);
+              *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < prm.N) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int ch = rnd * 2 + c;
+            if (ch < kChunks && ch * 32 < prm.d) tma_store_3d(&tm_o, stage + c * 1024, head * prm.d + ch * 32, row0, b);
+          }
+          bulk_commit_group();
+        }
+      }
+      if (tracer && warp == 0) phase[11] = clock64();
+      if (lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+    } else if (kStaged && vec_ok) {
+      // Same staging through the (dead) Q tile of this warpgroup, written out with ordinary 16-byte
+      // stores: 8 lanes cover one 128-byte row segment, 4 rows per instruction.
       float* stage = reinterpret_cast<float*>(sQ + t * C::kTileBytesQK) + (warp & 3) * 1024;  // 32 x 32 floats
       const int r_sub = lane >> 3, c4 = lane & 7;
       const int row0 = q_base + t * kBM + (warp & 3) * 32;          // first row of this warp
       float* out0 = prm.O + ((size_t)b * prm.N + row0) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d;
+      constexpr int kChunks = kD / 32;
+      uint32_t o[kChunks][32];
 #pragma unroll
-      for (int ch = 0; ch < kD / 32; ++ch) {
-        uint32_t o[32];
-        tmem_ld32(tO + ch * 32, o);
-        tmem_wait_ld();
+      for (int ch = 0; ch < kChunks; ++ch) tmem_ld32(tO + ch * 32, o[ch]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 v = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
-                                       __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
+          const float4 v = make_float4(__uint_as_float(o[ch][4 * j]) * inv, __uint_as_float(o[ch][4 * j + 1]) * inv,
+                                       __uint_as_float(o[ch][4 * j + 2]) * inv, __uint_as_float(o[ch][4 * j + 3]) * inv);
           *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
         }
         __syncwarp();
@@ -989,6 +1056,25 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
   return true;
 }
 
+// 3D fp32 tensor [d2][d1][d0] (d0 contiguous), box = [1][box1][box0], SWIZZLE_128B (box0 * 4 == 128).
+bool make_map_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                     uint32_t box0, uint32_t box1, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  const cuuint64_t gdim[3] = {d0, d1, d2};
+  const cuuint64_t gstride[2] = {d0 * 4, d0 * d1 * 4};
+  const cuuint32_t box[3] = {box0, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *err = "cuTensorMapEncodeTiled(output) failed with CUresult " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
 template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD>;
@@ -997,6 +1083,12 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   if (!make_map_2d(&tq, a.Qp, C::kEltQK, units * a.n_pad, kD, kBM, C::kAtomQK / C::kEltQK, err) ||
       !make_map_2d(&tk, a.Kp, C::kEltQK, units * a.n_pad, kD, kBN, C::kAtomQK / C::kEltQK, err) ||
       !make_map_2d(&tv, a.Vt, 2, units * kD, a.n_pad, kD, 64, err))
+    return false;
+  // output tensor map for the TMA-store epilogue (only when a 32-column chunk never straddles a head)
+  CUtensorMap to;
+  memset(&to, 0, sizeof(to));
+  const bool tma_store = (a.d % 32) == 0 && getenv("QMHA_NO_TMA_STORE") == nullptr;
+  if (tma_store && !make_map_3d_f32(&to, a.O, (uint64_t)a.H * a.d, (uint64_t)a.N, (uint64_t)a.B, 32, 32, err))
     return false;
   auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb>;
   // block mode keeps one float4 of constants per 32-key block of the unit behind the barriers
@@ -1025,8 +1117,9 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.n_half_steps = (a.N + kHN - 1) / kHN;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)a.d);
   p.debug_no_mma = getenv("QMHA_DEBUG_NO_MMA") != nullptr;
+  p.tma_store = tma_store ? 1 : 0;
   dim3 grid((a.N + 2 * kBM - 1) / (2 * kBM), (unsigned)units, 1);
-  kern<<<grid, kThreads, smem_bytes, a.stream>>>(tq, tk, tv, p);
+  kern<<<grid, kThreads, smem_bytes, a.stream>>>(tq, tk, tv, to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("attention launch: ") + cudaGetErrorString(e); return false; }
   return true;

@@ -21,6 +21,7 @@ struct AttnParams {
   int n_half_steps;     // ceil(N / 64): 64-key softmax/MMA half-steps
   float scale_log2;     // log2(e) / sqrt(d)
   int debug_no_mma;     // measurement aid: skip every tcgen05.mma (results are garbage)
+  int tma_store;        // epilogue writes the output with TMA tensor stores (needs d % 32 == 0)
 };
 
 struct AttnLaunch {

@@ -91,7 +91,7 @@ for kern in ("int8", "f16"):
     if kern == "int8" and d == 128:
         nt = (N + 63) // 64
         for v in (0,):
-            buf = np.zeros(9 * nt * 4 + 8, np.int64)
+            buf = np.zeros(9 * nt * 4 + 16, np.int64)
             rc = L.qmha_debug_attention_trace(C.c_void_p(Qp.data_ptr()), C.c_void_p(Kp.data_ptr()), C.c_void_p(Vt.data_ptr()),
                                               C.c_void_p(sc.data_ptr()), C.c_void_p(out.data_ptr()), B, N, dm, H, v,
                                               buf.ctypes.data_as(C.c_void_p))
@@ -103,6 +103,7 @@ for kern in ("int8", "f16"):
             np.save(os.path.join(OUT, f"trace_v{v}.npy"), tr)
             print("CTA phases (clk): setup %d, to first scores %d, main loop %d, wait O final %d, stores %d, exit barrier %d; total %d" % (
                 ph[1] - ph[0], ph[2] - ph[1], ph[3] - ph[2], ph[4] - ph[3], ph[5] - ph[4], ph[6] - ph[5], ph[6] - ph[0]), flush=True)
+            print("  epilogue detail (clk from O final): all tiles handed to the TMA %d, end %d" % tuple(int(ph[k] - ph[4]) for k in (11, 5)), flush=True)
             mid = slice(nt // 4, 3 * nt // 4)
             print(f"trace v{v}: median MMA iteration {np.median(np.diff(tr[8, mid, 0])):.0f} clk", flush=True)
             for w in range(8):
