@@ -374,6 +374,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     prefetch_tmap(&tm_q);
     prefetch_tmap(&tm_k);
     prefetch_tmap(&tm_v);
+    prefetch_tmap(&tm_o);
     mbar_init(&bars->q_full, 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars->k_full[i], 1);
@@ -901,40 +902,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ([B][N][H*d], box 1 x 32 x 32).  All TMEM loads are issued up front, one proxy fence per two tiles.
     if (kTmaStore && prm.tma_store) {
       mbar_wait(&bars->qk_done, 0, err_flag, 341 + t, dead);
-      float* stage = reinterpret_cast<float*>(sK) + warp * 2048;   // 2 x (32 rows x 32 floats) per warp
-      const int row0 = q_base + t * kBM + (warp & 3) * 32;
+      // The TMA needs ~1.2 k clk to read a staged tile, so re-using a staging tile costs that much.
+      // When the K and V rings together give every warp 16 KB, all (up to four) tiles of a warp are
+      // staged at once; the V ring is only free once the other query tile has finished as well.
+      constexpr int kRingBytes = C::kStagesK * C::kTileBytesQK + C::kStagesV * C::kTileBytesV;
       constexpr int kChunks = kD / 32;
-      uint32_t o[kChunks][32];
-#pragma unroll
-      for (int ch = 0; ch < kChunks; ++ch) tmem_ld32(tO + ch * 32, o[ch]);
-      tmem_wait_ld();
-#pragma unroll
-      for (int rnd = 0; rnd < (kChunks + 1) / 2; ++rnd) {
-        if (rnd > 0) {
-          if (lane == 0) bulk_wait_group_read<0>();  // the previous round's stores have read both tiles
+      constexpr int kBufs = (kRingBytes >= 8 * 4 * 4096 && kChunks > 2) ? 4 : 2;
+      if constexpr (kBufs == 4) {
+        mbar_wait(&bars->o_final[t ^ 1], 0, err_flag, 343 + t, dead);
+        tc_fence_after();
+      }
+      float* stage = reinterpret_cast<float*>(sK) + warp * (kBufs * 1024);   // kBufs x (32 rows x 32 floats)
+      const int row0 = q_base + t * kBM + (warp & 3) * 32;
+      // Rolled on purpose: this code runs once per CTA, straight out of a cold instruction cache, and
+      // its fetch — not its execution — is what it costs.
+#pragma unroll 1
+      for (int ch = 0; ch < kChunks; ++ch) {
+        if (ch >= kBufs) {
+          if (lane == 0) bulk_wait_group_read<kBufs - 1>();  // the store that used this tile has read it
           __syncwarp();
         }
+        float* buf = stage + (ch % kBufs) * 1024;
+        uint32_t o[32];
+        tmem_ld32(tO + ch * 32, o);
+        tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int ch = rnd * 2 + c;
-          if (ch < kChunks) {
-            float* buf = stage + c * 1024;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 v = make_float4(__uint_as_float(o[ch][4 * j]) * inv, __uint_as_float(o[ch][4 * j + 1]) * inv,
-                                           __uint_as_float(o[ch][4 * j + 2]) * inv, __uint_as_float(o[ch][4 * j + 3]) * inv);
-              *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
-            }
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
+                                       __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
+          *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && row0 < prm.N) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int ch = rnd * 2 + c;
-            if (ch < kChunks && ch * 32 < prm.d) tma_store_3d(&tm_o, stage + c * 1024, head * prm.d + ch * 32, row0, b);
-          }
+        if (lane == 0 && row0 < prm.N && ch * 32 < prm.d) {
+          tma_store_3d(&tm_o, buf, head * prm.d + ch * 32, row0, b);
           bulk_commit_group();
         }
       }
