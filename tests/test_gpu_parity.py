@@ -407,3 +407,20 @@ def test_repeated_runs_are_bit_identical(qm, torch, oracle, shape):
             torch.cuda.synchronize()
             assert torch.equal(first, again), (kern, gran)
     qm.binding.check_async_error()
+
+
+# ---------------------------------------------------------------------------------- short / ragged sequences
+@pytest.mark.parametrize("N", [1, 2, 63, 64, 65, 127, 129, 191, 192, 193, 255, 257, 320, 449])
+def test_every_pipeline_depth_and_ragged_tail(qm, torch, oracle, N):
+    """1 .. 8 half-steps (the pipeline prologue handles 1, 2 and 3 half-steps specially) with and
+    without a ragged last step, block / head scales and the FP16 kernel, against the FP64 oracle."""
+    dm, h = 256, 2
+    q, k, v = (a[None] for a in oracle.golden_inputs(N, dm, h))
+    ref = oracle.mha(q, k, v, h, "f64")
+    tq, tk, tv = _dev(torch, q, k, v)
+    for kern, gran, tol in (("int8", qm.GRAN_BLOCK, INT8_MAX_ABS), ("int8", qm.GRAN_HEAD, INT8_MAX_ABS),
+                            ("f16", qm.GRAN_HEAD, F16_MAX_ABS)):
+        out = qm.forward(tq, tk, tv, h, kernel=kern, gran=gran)
+        torch.cuda.synchronize()
+        qm.binding.check_async_error()
+        assert _err(out.cpu().numpy(), ref)[0] <= tol, (kern, gran)
