@@ -119,7 +119,7 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
  * row index within the batch entry, pairs (k, k + d/2), theta = powf(base, -2k/d) exactly as
  * verify.cu:9-23 / generate_golden.cpp:38-51.  The rotated values are bit-identical to the CPU
  * restatement (cos/sin come from a host-built table).  Needs d % 8 == 0 and, for INT8,
- * QMHA_GRAN_BLOCK.  Process-wide setting; QMHA_ROPE=1 in the environment enables it at start. */
+ * QMHA_GRAN_BLOCK or QMHA_GRAN_HEAD (per-tensor scales are not covered).  Process-wide setting; QMHA_ROPE=1 in the environment enables it at start. */
 int qmha_set_rope(int enable, float base);
 int qmha_get_rope(void);
 

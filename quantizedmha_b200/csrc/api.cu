@@ -207,8 +207,9 @@ int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, i
   a.stream = stream;
   if (rope_enabled()) {
     if ((d & 7) != 0) return fail("fused RoPE needs a head dimension that is a multiple of 8");
-    if (a.int8 && gran != QMHA_GRAN_BLOCK)
-      return fail("fused RoPE is implemented for QMHA_GRAN_BLOCK (INT8) and for the F16 kernel");
+    static const bool two_pass = getenv("QMHA_TWO_PASS_QUANT") != nullptr;
+    if (a.int8 && !(gran == QMHA_GRAN_BLOCK || (gran == QMHA_GRAN_HEAD && !two_pass)))
+      return fail("fused RoPE is implemented for QMHA_GRAN_BLOCK / QMHA_GRAN_HEAD (INT8) and for the F16 kernel");
     int dev = -1;
     cudaGetDevice(&dev);
     if (get_rope_table(dev, N, d, g_rope_base, &a.rope)) return 1;

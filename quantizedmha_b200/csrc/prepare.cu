@@ -440,7 +440,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kFusedThr
 fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                       const float* __restrict__ V, float* __restrict__ scales,
                       int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
-                      int N, int H, int d, int n_pad) {
+                      int N, int H, int d, int n_pad, const float2* __restrict__ rope) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) uint8_t fused_smem[];
@@ -467,7 +467,17 @@ fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
 
   // ---- phase 1: absmax over my rows
   float m = 0.f;
-  if (col_ok) {
+  const bool rotate = rope != nullptr && z < 2;   // fused RoPE on Q and K (uniform for the CTA)
+  if (rotate) {
+    // warp-uniform loop (the partner elements of the rotation come from other lanes by shuffle):
+    // every lane walks the same row slots and loads zeros where it has nothing
+    for (int r0 = r_begin; r0 < r_end; r0 += kRowsPerPass) {
+      const int r = r0 + rsub;
+      float4 x = (r < N && col_ok) ? ldg_f4(src + (size_t)r * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x = rope_rotate(x, vec, r, N, d, rope);
+      m = absmax4(m, x);
+    }
+  } else if (col_ok) {
     const float* col = src + vec * 4;
     int r = r_begin + rsub;
     const int r_stop = min(r_end, N);
@@ -515,6 +525,14 @@ fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
       float x[8][4];
 #pragma unroll
       for (int u = 0; u < 8; ++u) load4(n + u * kRowsPerPass, x[u]);
+      if (rotate) {  // same rotation as in phase 1, bit for bit
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 rr = rope_rotate(make_float4(x[u][0], x[u][1], x[u][2], x[u][3]), vec,
+                                        n + u * kRowsPerPass, N, d, rope);
+          x[u][0] = rr.x; x[u][1] = rr.y; x[u][2] = rr.z; x[u][3] = rr.w;
+        }
+      }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int nn = n + u * kRowsPerPass;
@@ -567,7 +585,7 @@ cudaError_t launch_fused_cfg(const PrepareArgs& a) {
   dim3 grid(kClusterSize, a.B * a.H, 3);
   kern<<<grid, kFusedThreads, kFusedSmemBytes, a.stream>>>(
       a.Q, a.K, a.V, a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
-      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad);
+      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
   return cudaGetLastError();
 }
 

@@ -379,10 +379,18 @@ def test_fused_rope_matches_the_cpu_reference_with_rope(qm, torch, oracle, shape
         qm.set_rope(False)
         host_rot = qm.forward(*_dev(torch, qr, kr, v), h, kernel="int8", gran=qm.GRAN_BLOCK)
         assert torch.equal(out, host_rot)
-        # unsupported combination fails loudly instead of silently skipping the rotation
+        # per-(batch, head) scales: same rotation inside the cluster quantiser, codes bit-exact as well
         qm.set_rope(True)
+        Qh, Kh, Vh, sch = qm.quantize_qkv(tq, tk, tv, h, qm.GRAN_HEAD)
+        for i, (x, packed) in enumerate(((qr, Qh), (kr, Kh))):
+            codes, s = oracle.quantize(x, h, "head")
+            assert np.array_equal(_unpack_rows(packed, B, N, h, d), codes), "QK"[i]
+            assert np.array_equal(sch[i].cpu().numpy(), s), "QK"[i]
+        outh = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_HEAD)
+        assert _err(outh.cpu().numpy(), ref)[0] <= INT8_MAX_ABS
+        # unsupported combination fails loudly instead of silently skipping the rotation
         with pytest.raises(qm.QmhaError):
-            qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_HEAD)
+            qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_TENSOR)
     finally:
         qm.set_rope(False)
     again = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_BLOCK)
