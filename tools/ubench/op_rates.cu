@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
-enum Op { VIMNMX3, VIMNMX2, FMNMX3, FMNMX2, VIADD_, LOP3_, FFMA2_, FADD2_, F2FP_, MUFU_, I2FP_, HMNMX2_, MUFU16_, MUFU16X2_, NOPS };
+enum Op { VIMNMX3, VIMNMX2, FMNMX3, FMNMX2, VIADD_, LOP3_, FFMA2_, FADD2_, F2FP_, MUFU_, I2FP_, HMNMX2_, MUFU16_, MUFU16X2_, HADD2_, NOPS };
 template <int OP>
 __global__ void __launch_bounds__(512, 1) k(int iters, long long* cyc, int* sink, int seed) {
   int a[8], b[8];
@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(512, 1) k(int iters, long long* cyc, int* sink
         if (OP == MUFU_) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__int_as_float(a[i]))); a[i] = __float_as_int(y); }
         if (OP == I2FP_) a[i] = __float_as_int((float)a[i]);
         if (OP == MUFU16_) { unsigned short h = (unsigned short)a[i], r; asm("ex2.approx.f16 %0, %1;" : "=h"(r) : "h"(h)); a[i] = r; }
+        if (OP == HADD2_) { uint32_t r; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a[i]), "r"(b[i])); a[i] = r; }
         if (OP == MUFU16X2_) { uint32_t r; asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a[i])); a[i] = r; }
         if (OP == HMNMX2_) { uint32_t r; asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a[i]), "r"(b[i])); a[i] = r; }
       }
@@ -66,6 +67,6 @@ int main() {
   run<VIMNMX3>("VIMNMX3", 32); run<VIMNMX2>("VIMNMX", 32); run<FMNMX3>("FMNMX3", 32); run<FMNMX2>("FMNMX", 32);
   run<VIADD_>("VIADD", 32); run<LOP3_>("LOP3", 32); run<FFMA2_>("FFMA2", 16); run<FADD2_>("FADD2", 16);
   run<F2FP_>("F2FP", 32); run<MUFU_>("MUFU.EX2", 32); run<I2FP_>("I2FP", 32); run<HMNMX2_>("HMNMX2", 32);
-  run<MUFU16_>("EX2.F16", 32); run<MUFU16X2_>("EX2.F16x2", 32);
+  run<MUFU16_>("EX2.F16", 32); run<MUFU16X2_>("EX2.F16x2", 32); run<HADD2_>("HADD2", 32);
   return 0;
 }
