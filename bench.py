@@ -179,6 +179,16 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # Bind this rank to the CPUs next to its GPU (NUMA node of the PCIe root): the pinned host buffers of
+    # the e2e arm are then first-touched in local memory instead of all ranks sharing one node.
+    numa = "default"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = "cpu affinity set to the GPU's local CPUs (nvml)"
+    except Exception:  # noqa: BLE001  (no nvml / not permitted: keep the default placement)
+        pass
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -345,6 +355,7 @@ def run_native(args):
                 "h2d_bytes_per_step": 3 * E * 4, "d2h_bytes_per_step": E * 4, "steps": e2e_steps,
                 "timed_batch_entries": Be, "of_batch_entries": Bl,
                 "api": "qmha_forward_host (pinned host buffers, copies pipelined per batch entry)",
+                "host_placement": numa,
                 "max_abs_vs_device_path": e2e_maxdiff},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -18,11 +18,11 @@ __global__ void __launch_bounds__(512, 1) k(int iters, long long* cyc, int* sink
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (OP == VIMNMX3) a[i] = max(max(a[i], b[i]), b[(i + 1) & 7] + u);
-        if (OP == VIMNMX2) a[i] = max(a[i], b[i] + u);
+        if (OP == VIMNMX2) a[i] = max(a[i], b[i]) ^ b[(i + 1) & 7];
         if (OP == FMNMX3) a[i] = __float_as_int(fmaxf(fmaxf(__int_as_float(a[i]), __int_as_float(b[i])), __int_as_float(b[(i + 1) & 7])));
-        if (OP == FMNMX2) a[i] = __float_as_int(fmaxf(__int_as_float(a[i]), __int_as_float(b[i])));
-        if (OP == VIADD_) a[i] = a[i] + 0x4B400000;
-        if (OP == LOP3_) a[i] = (a[i] ^ b[i]) | 0x1234;
+        if (OP == FMNMX2) a[i] = __float_as_int(fmaxf(__int_as_float(a[i]), __int_as_float(b[i])) + __int_as_float(b[(i + 1) & 7]));
+        if (OP == VIADD_) a[i] = a[i] + b[i];
+        if (OP == LOP3_) a[i] = (a[i] ^ b[i]) | b[(i + 3) & 7];
         if (OP == FFMA2_ || OP == FADD2_) {
           if ((i & 1) == 0) {
             uint64_t x, y, z;
