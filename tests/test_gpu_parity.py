@@ -432,3 +432,65 @@ def test_every_pipeline_depth_and_ragged_tail(qm, torch, oracle, N):
         torch.cuda.synchronize()
         qm.binding.check_async_error()
         assert _err(out.cpu().numpy(), ref)[0] <= tol, (kern, gran)
+
+
+# ---------------------------------------------------------------------------------- guard bands
+# (compute-sanitizer is not available on the GPU pool: the write footprint is checked here instead)
+@pytest.mark.parametrize("shape", [(1, 1, 32, 1), (2, 300, 128, 2), (1, 449, 256, 2), (2, 257, 96, 1),
+                                   (1, 130, 128, 4), (3, 64, 40, 1), (1, 100, 50, 1), (1, 513, 21, 3)])
+def test_output_writes_stay_inside_the_output_tensor(qm, torch, oracle, shape):
+    """The output lives in the middle of a larger allocation filled with a sentinel bit pattern: after
+    a forward (TMA tensor stores clipped at N, staged row stores for d % 32 != 0, every scale mode and
+    the FP16 kernel) the sentinels on both sides are untouched, every output element was written, and
+    the result equals the one computed into a free-standing tensor."""
+    B, N, dm, h = shape
+    q, k, v = oracle.profile_inputs(B * N, dm)
+    tq, tk, tv = _dev(torch, *(a.reshape(B, N, dm) for a in (q, k, v)))
+    n = B * N * dm
+    pad = 4096 + 64  # floats on each side; keeps the 16-byte alignment of the output
+    sentinel = -1234567.0
+    modes = [("f16", qm.GRAN_HEAD), ("int8", qm.GRAN_HEAD), ("int8", qm.GRAN_TENSOR)]
+    if (dm // h) % 4 == 0:  # block scales need d % 4 == 0 (they fail loudly otherwise)
+        modes.append(("int8", qm.GRAN_BLOCK))
+    for kern, gran in modes:
+        buf = torch.full((n + 2 * pad,), sentinel, device=tq.device)
+        out = buf[pad:pad + n].view(B, N, dm)
+        qm.forward(tq, tk, tv, h, kernel=kern, gran=gran, out=out)
+        torch.cuda.synchronize()
+        qm.binding.check_async_error()
+        assert bool((buf[:pad] == sentinel).all()) and bool((buf[pad + n:] == sentinel).all()), (kern, gran)
+        assert not bool((out == sentinel).any()), (kern, gran, "unwritten output elements")
+        free = qm.forward(tq, tk, tv, h, kernel=kern, gran=gran)
+        torch.cuda.synchronize()
+        assert torch.equal(out, free), (kern, gran)
+
+
+@pytest.mark.parametrize("gran_name", ["GRAN_BLOCK", "GRAN_HEAD"])
+def test_prepared_operand_writes_stay_inside_their_tensors(qm, torch, oracle, gran_name):
+    """Same for the quantise kernel: Qp / Kp / Vt / scales are carved out of sentinel-filled byte
+    buffers; the bytes around them survive and the padding rows / columns are written as zeros."""
+    import ctypes as C
+    gran = getattr(qm, gran_name)
+    B, N, dm, h = 2, 300, 128, 2
+    q, k, v = oracle.profile_inputs(B * N, dm)
+    tq, tk, tv = _dev(torch, *(a.reshape(B, N, dm) for a in (q, k, v)))
+    n_pad, d_pad = qm.workspace_dims(N, dm, h)
+    u = B * h
+    guard = 8192
+    sizes = {"Qp": u * n_pad * d_pad, "Kp": u * n_pad * d_pad, "Vt": u * d_pad * n_pad * 2,
+             "sc": 3 * u * (n_pad // 32 if gran == qm.GRAN_BLOCK else 1) * 4}
+    bufs = {name: torch.full((sz + 2 * guard,), 0x5A, dtype=torch.uint8, device=tq.device) for name, sz in sizes.items()}
+    ptr = {name: b.data_ptr() + guard for name, b in bufs.items()}
+    rc = qm.lib().qmha_quantize_qkv(C.c_void_p(tq.data_ptr()), C.c_void_p(tk.data_ptr()), C.c_void_p(tv.data_ptr()),
+                                    B, N, dm, h, gran, C.c_void_p(ptr["Qp"]), C.c_void_p(ptr["Kp"]),
+                                    C.c_void_p(ptr["Vt"]), C.c_void_p(ptr["sc"]), C.c_void_p(0))
+    assert rc == 0, qm.binding.lib().qmha_last_error()
+    torch.cuda.synchronize()
+    for name, b in bufs.items():
+        assert bool((b[:guard] == 0x5A).all()) and bool((b[guard + sizes[name]:] == 0x5A).all()), name
+    Qp = bufs["Qp"][guard:guard + sizes["Qp"]].view(torch.int8).view(u, n_pad, d_pad)
+    assert not bool(Qp[:, N:, :].any()), "padding rows of Qp must be zero"
+    Qr, Kr, Vr, sr = qm.quantize_qkv(tq, tk, tv, h, gran)
+    assert torch.equal(Qp, Qr)
+    Vt = bufs["Vt"][guard:guard + sizes["Vt"]].view(torch.float16).view(u, d_pad, n_pad)
+    assert torch.equal(Vt, Vr) and not bool(Vt[:, :, N:].any())
