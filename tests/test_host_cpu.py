@@ -147,3 +147,25 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "TFLOP/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_compare_ncu_report_on_the_committed_summaries():
+    """tools/compare_ncu.py (the reference's tools/compare_ncu.py does the same on text
+    tables): metric union, unit normalisation and delta columns, on the ncu summaries under profiles/."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("compare_ncu", os.path.join(root, "tools", "compare_ncu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    a = mod.load(os.path.join(root, "profiles", "r01", "ncu_attn_fwd_int8_block_c4.txt"))
+    b = mod.load(os.path.join(root, "profiles", "r01", "ncu_block_quantize_c4.txt"))
+    assert a["gpu__time_duration.sum"][1] == "s" and 1e-3 < a["gpu__time_duration.sum"][0] < 1e-2   # ms -> s
+    assert b["gpu__time_duration.sum"][0] < 1e-3                                                     # us -> s
+    assert a["dram__bytes_read.sum"][1] == "byte" and a["dram__bytes_read.sum"][0] > 1e9
+    md = mod.report([a, b], ["attn", "quant"])
+    row = next(l for l in md.splitlines() if "gpu__time_duration.sum" in l)
+    assert row.count("|") == 6 and row.rstrip().endswith("% |") and "-8" in row   # quant is ~86 % shorter
+    raw = ('"ID","Kernel Name","gpu__time_duration.sum","dram__bytes_read.sum"\n"","","us","Mbyte"\n'
+           '"0","k_a","10","2"\n"1","k_b","30","4"\n"2","k_a","20","6"\n')
+    c = mod.parse_raw_csv(raw, kernel="k_a")
+    assert abs(c["gpu__time_duration.sum"][0] - 15e-6) < 1e-12 and c["dram__bytes_read.sum"] == (4e6, "byte")
