@@ -437,7 +437,8 @@ def test_every_pipeline_depth_and_ragged_tail(qm, torch, oracle, N):
 # ---------------------------------------------------------------------------------- guard bands
 # (compute-sanitizer is not available on the GPU pool: the write footprint is checked here instead)
 @pytest.mark.parametrize("shape", [(1, 1, 32, 1), (2, 300, 128, 2), (1, 449, 256, 2), (2, 257, 96, 1),
-                                   (1, 130, 128, 4), (3, 64, 40, 1), (1, 100, 50, 1), (1, 513, 21, 3)])
+                                   (1, 130, 128, 4), (3, 64, 40, 1), (1, 100, 50, 1), (1, 513, 21, 3), (1, 5, 3, 3),
+                                   (1, 1, 1, 1)])
 def test_output_writes_stay_inside_the_output_tensor(qm, torch, oracle, shape):
     """The output lives in the middle of a larger allocation filled with a sentinel bit pattern: after
     a forward (TMA tensor stores clipped at N, staged row stores for d % 32 != 0, every scale mode and
@@ -463,6 +464,8 @@ def test_output_writes_stay_inside_the_output_tensor(qm, torch, oracle, shape):
         free = qm.forward(tq, tk, tv, h, kernel=kern, gran=gran)
         torch.cuda.synchronize()
         assert torch.equal(out, free), (kern, gran)
+        ref = oracle.mha(*(a.reshape(B, N, dm) for a in (q, k, v)), h, "f64")
+        assert _err(out.cpu().numpy(), ref)[0] <= (F16_MAX_ABS if kern == "f16" else INT8_MAX_ABS), (kern, gran)
 
 
 @pytest.mark.parametrize("gran_name", ["GRAN_BLOCK", "GRAN_HEAD"])

@@ -85,9 +85,11 @@ def load(path, kernel=None):
     return parse_summary(text)
 
 
-def _fmt(v):
+def _fmt(v, unit=""):
     if v is None:
         return "–"
+    if (unit not in ("byte", "s", "hz", "cycle", "inst")) or (unit == "inst" and abs(v) < 1e3):   # percentages, ratios, counts: as they are
+        return f"{v:.4g}"
     a = abs(v)
     if a >= 1e9:
         return f"{v / 1e9:.3f} G"
@@ -120,7 +122,7 @@ def report(caps, names, keep_all=False):
                 deltas.append("–")
             else:
                 deltas.append(f"{(v / vals[0] - 1) * 100:+.1f} %")
-        lines.append("| " + " | ".join([f"`{k}`", unit] + [_fmt(v) for v in vals] + deltas) + " |")
+        lines.append("| " + " | ".join([f"`{k}`", unit] + [_fmt(v, unit) for v in vals] + deltas) + " |")
     return "\n".join(lines) + "\n"
 
 
