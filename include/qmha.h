@@ -52,7 +52,12 @@ void solve(const float* Q, const float* K, const float* V, float* output, int N,
 /* ---- extended, stream-ordered entry --------------------------------------------------------
  * Q,K,V,O: DEVICE pointers, fp32, contiguous [B, N, d_model].  `stream` is a cudaStream_t
  * (NULL = legacy default stream).  Asynchronous: returns after enqueueing.  Scratch (int8 /
- * fp16 operands, scales) lives in a per-device workspace grown on demand and reused. */
+ * fp16 operands, scales) lives in a per-device workspace grown on demand and reused.
+ * Threading / streams: entry points may be called from several host threads and on different streams
+ * of one device; calls that use the workspace are serialised on the host for the duration of their
+ * enqueue and ordered on the device behind the previous user of the workspace (an event wait when the
+ * stream differs), so concurrent callers get correct results but do not overlap on one GPU.
+ * qmha_shutdown() must not run concurrently with other calls. */
 int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B, int N,
                  int d_model, int h, int kernel, int gran, void* stream);
 

@@ -54,8 +54,35 @@ struct Workspace {
   float2* rope_tab = nullptr;  // {cos, sin}[rope_n][rope_d/2] for rope_base
   int rope_n = 0, rope_d = 0;
   float rope_base = 0.f;
+  // The workspace is shared by every call on the device.  `call_mu` serialises the host-side enqueue
+  // sequences (and any growth) of concurrent callers; `last_use` is recorded behind the last enqueued
+  // work that touches the workspace, and a call on another stream waits for it on the device first
+  // (WorkspaceUse), so asynchronous calls on different streams cannot overwrite each other's operands.
+  std::mutex call_mu;
+  cudaEvent_t last_use = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool in_flight = false;
 };
 std::map<int, Workspace> g_ws;  // per device
+
+// Holds a workspace for one enqueue sequence on stream `s` (see Workspace::call_mu / last_use).
+struct WorkspaceUse {
+  Workspace* w = nullptr;
+  cudaStream_t s = nullptr;
+  std::unique_lock<std::mutex> lk;
+  bool armed = false;
+  // takes over the lock acquired by get_workspace()
+  void begin(Workspace* w_, std::unique_lock<std::mutex>&& lk_, cudaStream_t s_) {
+    w = w_; s = s_; lk = std::move(lk_);
+    if (w->in_flight && w->last_stream != s) cudaStreamWaitEvent(s, w->last_use, 0);
+    armed = true;
+  }
+  ~WorkspaceUse() {
+    if (!armed) return;
+    if (!w->last_use && cudaEventCreateWithFlags(&w->last_use, cudaEventDisableTiming) != cudaSuccess) return;
+    if (cudaEventRecord(w->last_use, s) == cudaSuccess) { w->last_stream = s; w->in_flight = true; }
+  }
+};
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -89,9 +116,16 @@ int require_device() {
 // Grows (never shrinks) the calling device's workspace.  cudaMalloc only on growth, so steady
 // state has no allocation in the timed path (the reference mallocs per head per call,
 // launchers.h:27-39 and fa_tc_int8_b.cu:589-597).
-int get_workspace(int dev, size_t qk_bytes, size_t vt_bytes, size_t scale_elems, Workspace** out) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  Workspace& w = g_ws[dev];
+// Returns with the workspace's call lock held (`call_lock`), which also covers the growth below.
+int get_workspace(int dev, size_t qk_bytes, size_t vt_bytes, size_t scale_elems, Workspace** out,
+                  std::unique_lock<std::mutex>* call_lock) {
+  Workspace* wp;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    wp = &g_ws[dev];   // std::map nodes never move
+  }
+  Workspace& w = *wp;
+  *call_lock = std::unique_lock<std::mutex>(w.call_mu);
   cudaError_t e;
   if (!w.error_flag) {
     if ((e = cudaMalloc(&w.error_flag, sizeof(int))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
@@ -344,9 +378,12 @@ int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int
                       void* stream) {
   const int dev = require_device();
   if (dev < 0) return 1;
-  Workspace* w;
-  if (get_workspace(dev, 0, 0, (size_t)3 * B * h, &w)) return 1;
   if (gran != QMHA_GRAN_TENSOR && gran != QMHA_GRAN_HEAD && gran != QMHA_GRAN_BLOCK) return fail("unknown scale granularity");
+  Workspace* w;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 0, 0, (size_t)3 * B * h, &w, &call_lock)) return 1;
+  WorkspaceUse use;
+  use.begin(w, std::move(call_lock), (cudaStream_t)stream);
   if (prepare_impl(Q, K, V, B, N, d_model, h, QMHA_KERNEL_INT8, gran, Qp, Kp, Vt, scales, w->amax,
                    (cudaStream_t)stream))
     return 1;
@@ -400,7 +437,10 @@ int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt, 
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   Workspace* w;
-  if (get_workspace(dev, 0, 0, scale_count(B * h, n_pad, gran), &w)) return 1;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 0, 0, scale_count(B * h, n_pad, gran), &w, &call_lock)) return 1;
+  WorkspaceUse use;
+  use.begin(w, std::move(call_lock), (cudaStream_t)stream);
   if (attention_impl(Qp, Kp, Vt, scales, O, B, N, d_model, h, kernel, w->error_flag,
                      (cudaStream_t)stream, nullptr, -1, gran, w->aux, w->vmax))
     return 1;
@@ -418,10 +458,13 @@ int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B
   const size_t units = (size_t)B * h;
   const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
   Workspace* w;
+  std::unique_lock<std::mutex> call_lock;
   if (get_workspace(dev, units * n_pad * d_pad * elt, units * n_pad * d_pad * 2,
-                    scale_count((int)units, n_pad, gran), &w))
+                    scale_count((int)units, n_pad, gran), &w, &call_lock))
     return 1;
   cudaStream_t s = (cudaStream_t)stream;
+  WorkspaceUse use;   // orders this call behind earlier work on other streams that uses the workspace
+  use.begin(w, std::move(call_lock), s);
   if (prepare_impl(Q, K, V, B, N, d_model, h, kernel, gran, w->Qp, w->Kp, w->Vt, w->scales, w->amax, s))
     return 1;
   if (attention_impl(w->Qp, w->Kp, w->Vt, w->scales, O, B, N, d_model, h, kernel, w->error_flag, s,
@@ -440,7 +483,10 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
   const int dev = require_device();
   if (dev < 0) return 1;
   Workspace* w;
-  if (get_workspace(dev, 0, 0, 0, &w)) return 1;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 0, 0, 0, &w, &call_lock)) return 1;
+  WorkspaceUse use;
+  use.begin(w, std::move(call_lock), nullptr);
   const size_t n = (size_t)9 * ((N + 63) / 64) * 4 + 16;
   long long* dtrace = nullptr;
   cudaError_t e = cudaMalloc(&dtrace, n * sizeof(long long));
@@ -463,7 +509,8 @@ int qmha_check_async_error(void) {
   const int dev = require_device();
   if (dev < 0) return 1;
   Workspace* w;
-  if (get_workspace(dev, 0, 0, 0, &w)) return 1;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 0, 0, 0, &w, &call_lock)) return 1;
   if (check_error_flag(w)) return 1;
   g_err.clear();
   return 0;
@@ -500,6 +547,15 @@ int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, 
   const size_t slab = (size_t)N * d_model;  // elements per batch entry
   cudaError_t e;
   std::vector<Slot>* slots;
+  // Each slot needs its own operand workspace region: the slot streams run against disjoint halves.
+  // The workspace's call lock is held for the whole (synchronous) call: it also guards the staging slots.
+  const size_t units1 = (size_t)h;
+  const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
+  const size_t qk1 = units1 * n_pad * d_pad * elt, vt1 = units1 * n_pad * d_pad * 2;
+  const size_t sc1 = scale_count((int)units1, n_pad, gran);
+  Workspace* w;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 2 * qk1, 2 * vt1, 2 * sc1, &w, &call_lock)) return 1;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto& st = staging[dev];
@@ -519,13 +575,9 @@ int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, 
     }
     slots = &st.second;
   }
-  // Each slot needs its own operand workspace region: run slot streams against disjoint halves.
-  const size_t units1 = (size_t)h;
-  const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
-  const size_t qk1 = units1 * n_pad * d_pad * elt, vt1 = units1 * n_pad * d_pad * 2;
-  Workspace* w;
-  const size_t sc1 = scale_count((int)units1, n_pad, gran);
-  if (get_workspace(dev, 2 * qk1, 2 * vt1, 2 * sc1, &w)) return 1;
+  // earlier asynchronous calls (qmha_forward on a caller stream) may still be using the workspace
+  if (w->in_flight)
+    for (auto& sl : *slots) cudaStreamWaitEvent(sl.s, w->last_use, 0);
   for (int b = 0; b < B; ++b) {
     Slot& sl = (*slots)[b & 1];
     const size_t off = (size_t)b * slab;
@@ -549,6 +601,7 @@ int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, 
   }
   for (auto& sl : *slots)
     if ((e = cudaStreamSynchronize(sl.s)) != cudaSuccess) return fail_cuda("forward_host sync", e);
+  w->in_flight = false;   // everything that used the workspace, this call's and earlier work, has completed
   if (check_error_flag(w)) return 1;
   g_err.clear();
   return 0;
@@ -563,6 +616,7 @@ void qmha_shutdown(void) {
     Workspace& w = kv.second;
     cudaFree(w.Qp); cudaFree(w.Kp); cudaFree(w.Vt); cudaFree(w.scales); cudaFree(w.amax); cudaFree(w.aux); cudaFree(w.vmax);
     cudaFree(w.error_flag); cudaFree(w.rope_tab);
+    if (w.last_use) cudaEventDestroy(w.last_use);
   }
   g_ws.clear();
   cudaSetDevice(cur);

@@ -497,3 +497,57 @@ def test_prepared_operand_writes_stay_inside_their_tensors(qm, torch, oracle, gr
     assert torch.equal(Qp, Qr)
     Vt = bufs["Vt"][guard:guard + sizes["Vt"]].view(torch.float16).view(u, d_pad, n_pad)
     assert torch.equal(Vt, Vr) and not bool(Vt[:, :, N:].any())
+
+
+# ---------------------------------------------------------------------------------- shared workspace
+def test_calls_on_different_streams_and_threads_do_not_share_operands(qm, torch, oracle):
+    """The prepared operands live in one per-device workspace.  Asynchronous calls on different
+    (non-blocking) streams, issued back to back or from two host threads, must still produce what the
+    same calls produce one at a time: the library orders them on the device (Workspace::last_use)."""
+    import threading
+    B, N, dm, h = 2, 2048, 1024, 8
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    sets = [tuple(torch.rand((B, N, dm), device="cuda", generator=gen) * (i + 1) for _ in range(3)) for i in range(3)]
+    serial = []
+    for q, k, v in sets:
+        serial.append(qm.forward(q, k, v, h, kernel="int8", gran=qm.GRAN_BLOCK).clone())
+        torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in sets]
+    for rep in range(4):
+        outs = [torch.empty_like(s) for s in serial]
+        for (q, k, v), st, o in zip(sets, streams, outs):
+            qm.forward(q, k, v, h, kernel="int8", gran=qm.GRAN_BLOCK, out=o, stream=st)
+        torch.cuda.synchronize()
+        for o, s in zip(outs, serial):
+            assert torch.equal(o, s), f"back-to-back calls on different streams, repetition {rep}"
+    # two host threads, each with its own stream and inputs
+    outs = [torch.empty_like(s) for s in serial]
+    errs = []
+
+    def worker(i):
+        try:
+            for _ in range(6):
+                qm.forward(*sets[i], h, kernel="int8", gran=qm.GRAN_BLOCK, out=outs[i], stream=streams[i])
+        except Exception as exc:  # noqa: BLE001
+            errs.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errs, errs
+    qm.binding.check_async_error()
+    for o, s in zip(outs, serial):
+        assert torch.equal(o, s), "concurrent host threads"
+    # a synchronous host-buffer call right behind an asynchronous one
+    o_async = torch.empty_like(serial[0])
+    qm.forward(*sets[0], h, kernel="int8", gran=qm.GRAN_HEAD, out=o_async, stream=streams[0])
+    hq, hk, hv = (t.cpu() for t in sets[1])
+    o_host = qm.forward_host(hq, hk, hv, h, kernel="int8", gran=qm.GRAN_HEAD)
+    torch.cuda.synchronize()
+    ref0 = qm.forward(*sets[0], h, kernel="int8", gran=qm.GRAN_HEAD)
+    ref1 = qm.forward(*sets[1], h, kernel="int8", gran=qm.GRAN_HEAD)
+    torch.cuda.synchronize()
+    assert torch.equal(o_async, ref0) and torch.equal(torch.as_tensor(o_host).cuda(), ref1)
