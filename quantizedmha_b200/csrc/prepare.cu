@@ -244,15 +244,23 @@ prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
 // ------------------------------------------------------------------------------------------------
 // block_quantize_kernel: the reference's own granularity — one scale per (batch, head, 32-row
 // block), exactly fp32_to_int8sram on a Br x d / Bc x d tile (fa_tc_int8_b.cu:484,496,518) — in
-// ONE pass: a CTA keeps its 128-row tile (4 blocks) in registers, reduces the four block maxima,
+// ONE pass: a CTA keeps its kBlkRows-row tile (kBlkRows/32 blocks) in registers, reduces the block maxima,
 // then quantises from registers.  HBM traffic = algorithmic (read fp32 once, write codes once).
-//   grid = (n_pad/128, B*H, 3);  scales[z][unit][n_pad/32]
-// kRows = rows per CTA (a multiple of 32): 64 keeps the tile at 8 float4 per thread (<= 64 registers), so four
-// CTAs are resident per SM and the load phase of one overlaps the reduce / store phases of the others
-// (with 128 rows the kernel needs 99 registers, two CTAs per SM, and leaves HBM idle between phases).
-constexpr int kBlkRows = 64;
-template <int kD>
-__global__ void __launch_bounds__(kPrepThreads, 3)
+//   grid = (n_pad/kBlkRows, B*H, 3);  scales[z][unit][n_pad/32]
+// kBlkRows = rows per CTA (a multiple of 32): 64 keeps the tile at 8 float4 per thread.  Occupancy decides this
+// kernel (measured at B8/H32/N8192/d128, same box, ms per pass): 128 rows x 2 CTAs/SM 0.83, 64 x 3 (78 registers)
+// 0.81, 64 x 4 (64 registers) 0.73, 64 x 5 (48) 0.75, 64 x 6 (40 registers, 16 bytes of spill) 0.65 = the HBM
+// copy peak, 64 x 8 (32 registers, 132 bytes of spill) 0.88, 32 x 8 0.70.  The RoPE instantiation keeps the
+// three-CTA budget (it needs the registers for the rotation).
+#ifndef QMHA_BLKQ_ROWS
+#define QMHA_BLKQ_ROWS 64
+#endif
+constexpr int kBlkRows = QMHA_BLKQ_ROWS;
+#ifndef QMHA_BLKQ_CTAS
+#define QMHA_BLKQ_CTAS 6
+#endif
+template <int kD, bool kRope>
+__global__ void __launch_bounds__(kPrepThreads, kRope ? 3 : QMHA_BLKQ_CTAS)
 block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                       const float* __restrict__ V, float* __restrict__ scales,
                       int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
@@ -279,10 +287,12 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
     const int n = n0 + rsub + k * kRowsPerIter;
     x[k] = (n < N && col_ok) ? ldg_f4(src + (size_t)n * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (rope && z < 2) {  // rotate Q and K rows before the block maxima are taken (uniform branch)
+  if constexpr (kRope) {
+    if (z < 2) {  // rotate Q and K rows before the block maxima are taken (uniform branch)
 #pragma unroll
-    for (int k = 0; k < kLoads; ++k)
-      x[k] = rope_rotate(x[k], vec, n0 + rsub + k * kRowsPerIter, N, d, rope);
+      for (int k = 0; k < kLoads; ++k)
+        x[k] = rope_rotate(x[k], vec, n0 + rsub + k * kRowsPerIter, N, d, rope);
+    }
   }
   // block maxima: thread -> warp (shuffle) -> CTA (shared memory)
   __shared__ float s_max[kPrepThreads / 32][kBlocks];
@@ -350,7 +360,9 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
 template <int kD>
 cudaError_t launch_block_cfg(const PrepareArgs& a) {
   dim3 grid(a.n_pad / kBlkRows, a.B * a.H, 3);
-  block_quantize_kernel<kD><<<grid, kPrepThreads, 0, a.stream>>>(
+  // the RoPE variant is a separate instantiation: the plain one stays inside its register budget
+  auto kern = a.rope ? block_quantize_kernel<kD, true> : block_quantize_kernel<kD, false>;
+  kern<<<grid, kPrepThreads, 0, a.stream>>>(
       a.Q, a.K, a.V, a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
       reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
   return cudaGetLastError();

@@ -1,7 +1,10 @@
+# End-of-session check on the GPU box: full GPU test suite, default bench line, ncu launch list of the
+# same bench command and one full ncu capture of the block quantiser.  Outputs under gpurun_out/.
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/final_pytest.log
 python bench.py > gpurun_out/final_bench.log 2> gpurun_out/final_bench.err
-python bench.py --workload c4f16 --no-cpu-baseline > gpurun_out/final_bench_f16.log 2> gpurun_out/final_bench_f16.err
-python tools/prof_one.py f16 8,32,8192,128 2 > gpurun_out/prof_f16_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:attn_fwd -c 1 -f -o gpurun_out/prof_attn_f16 python tools/prof_one.py f16 8,32,8192,128 2 > gpurun_out/prof_f16_ncu.log 2>&1
-cat gpurun_out/final_pytest.log; tail -c 600 gpurun_out/final_bench.log; tail -c 300 gpurun_out/final_bench_f16.log
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 > gpurun_out/b_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_launches.log 2>&1
+python tools/prof_one.py int8 8,32,8192,128 1 block > gpurun_out/prof_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:block_quantize -c 1 -f -o gpurun_out/prof_blockq_final python tools/prof_one.py int8 8,32,8192,128 1 block > gpurun_out/prof_blockq_ncu.log 2>&1
+cat gpurun_out/final_pytest.log; tail -c 400 gpurun_out/final_bench.log
