@@ -5,12 +5,14 @@ B8/H32/N8192/d128 INT8).
     python bench.py --gpus N --steps K --warmup W          # this framework (CUDA, sm_100a)
     python bench.py --impl reference --steps K --warmup W  # the reference's CPU path, host cores
 
-One "step" = one pass of the hot path (INT8 quantise kernels + fused attention kernel, i.e. what
+One "step" = one pass of the hot path (INT8 quantise kernel + fused attention kernel, i.e. what
 qmha_forward()/solve() enqueue) over one batch of synthetic inputs resident in HBM.  Under
-torchrun (N>1) every rank owns its own (batch × head) units — no collective on the data path —
-and the time is the max over ranks of the CUDA-event time of the K steps.
+torchrun (N>1) every rank owns its own (batch x head) units — no collective on the data path —
+and the time is the max over ranks of the CUDA-event time of the K steps.  With N>1 the same
+process also times BASELINE config 5 (B=32, N=16384) split over the ranks — the strong-scaling
+sweep — and attaches it as `scaling_c5`.
 
-Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definition of every field.
+Prints ONE JSON line (rank 0).  See DESIGN.md §6 for the definition of every field.
 """
 import argparse
 import json
@@ -29,18 +31,24 @@ WORKLOADS = {
     "c3": (1, 8, 4096, 64, "int8", "weak"),      # reference fa_tc_int8_b comparison shape
     "c2": (1, 32, 8192, 32, "f16", "weak"),      # reference default config.h shape, FP16 anchor
     "c4f16": (8, 32, 8192, 128, "f16", "weak"),  # FP16 anchor at the headline shape
+    "c4bf16": (8, 32, 8192, 128, "bf16", "weak"),  # BF16 anchor at the headline shape
     "c5": (32, 32, 16384, 128, "int8", "strong"),  # long-context sweep: units split over ranks
 }
-METRIC = "attention fwd TFLOP/s at B8/H32/N8192/d128 INT8 (4*B*H*N^2*d FLOPs per step)"
+N_SM, MUFU_PER_SM_CLK = 148, 16   # B200: 148 SMs, 16 ex2 per SM per clock (4 per sub-partition)
+
+
+def metric_name(workload):
+    B, H, N, d, kernel, _ = WORKLOADS[workload]
+    return f"attention fwd TFLOP/s at B{B}/H{H}/N{N}/d{d} {kernel.upper()} (4*B*H*N^2*d FLOPs per step)"
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"src": "measured", "hbm": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
+        return {"src": "MEASURED_PEAKS.json", "hbm": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
                 "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"])}
-    return {"src": "fallback", "hbm": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0}
+    return {"src": "fallback of B200_PROFILING.md", "hbm": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -50,7 +58,6 @@ def peaks():
 def cpu_step(n, d, heads, threads):
     """Runs `heads` independent single-head attention problems [n, d] on `threads` host threads.
     Returns (seconds, kind)."""
-    import numpy as np
     from oracle import load_oracle, load_ref
     orc = load_oracle()
     ref = load_ref()
@@ -106,7 +113,7 @@ def run_reference(args):
     flops = 4.0 * heads * n * n * d
     val = flops / (ms / 1e3) / 1e12
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.workload), "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: B={B} H={H} N={N} d={d}; CPU step = bounded sample of "
@@ -163,9 +170,143 @@ class ClockSampler:
             for nm, val in zip(names, r[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        # "under load" = samples in the upper half of the observed power range (the sampler also sees idle time)
+        if pw:
+            thr = 0.5 * (min(pw) + max(pw))
+            sm_load = sorted(s for s, p in zip(sm, pw) if p >= thr) or sorted(sm)
+        else:
+            sm_load = sorted(sm)
+        return {"sm_mhz": sm_load[len(sm_load) // 2] if sm_load else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class Job:
+    """Inputs, prepared operands and output of one workload on one GPU, driven through the C-ABI."""
+
+    def __init__(self, torch, qm, dev, Bl, H, N, d, kernel, gran, seed, family="uniform"):
+        self.torch, self.qm, self.L = torch, qm, qm.lib()
+        self.Bl, self.H, self.N, self.d, self.kernel, self.gran = Bl, H, N, d, kernel, gran
+        self.dm = H * d
+        self.kid = qm.kernel_id(kernel)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        shape = (Bl, N, self.dm)
+        self.tq, self.tk, self.tv = (torch.empty(shape, device=dev) for _ in range(3))
+        self.fill(family, gen)
+        self.out = torch.empty(shape, device=dev)
+        n_pad, d_pad = qm.workspace_dims(N, self.dm, H)
+        units = Bl * H
+        elt = torch.int8 if kernel == "int8" else torch.float16   # bf16 operands are 2 bytes as well
+        self.Qp = torch.empty((units, n_pad, d_pad), dtype=elt, device=dev)
+        self.Kp = torch.empty_like(self.Qp)
+        self.Vt = torch.empty((units, d_pad, n_pad), dtype=torch.float16, device=dev)
+        self.sc = torch.empty((3, units, n_pad // 32) if gran == qm.GRAN_BLOCK else (3, units), dtype=torch.float32, device=dev)
+        self.stream = torch.cuda.current_stream()
+        self.sp = int(self.stream.cuda_stream)
+
+    def fill(self, family, gen):
+        for t in (self.tq, self.tk, self.tv):
+            if family == "uniform":     # U[0,1) like inputs/data.cu:15-22 (counter-based device RNG for the multi-GB shape)
+                t.uniform_(0.0, 1.0, generator=gen)
+            else:                       # 0.5*N(0,1) like tests/generate_golden.cpp:123-138: signed scores, moving row max
+                t.normal_(0.0, 0.5, generator=gen)
+
+    def chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.qmha_last_error().decode())
+
+    def prep(self):
+        if self.kernel == "int8":
+            self.chk(self.L.qmha_quantize_qkv(self.tq.data_ptr(), self.tk.data_ptr(), self.tv.data_ptr(), self.Bl, self.N,
+                                              self.dm, self.H, self.gran, self.Qp.data_ptr(), self.Kp.data_ptr(),
+                                              self.Vt.data_ptr(), self.sc.data_ptr(), self.sp))
+        else:
+            self.chk(self.L.qmha_convert_qkv_16(self.tq.data_ptr(), self.tk.data_ptr(), self.tv.data_ptr(), self.Bl, self.N,
+                                                self.dm, self.H, self.kid, self.Qp.data_ptr(), self.Kp.data_ptr(),
+                                                self.Vt.data_ptr(), self.sp))
+
+    def attn(self):
+        self.chk(self.L.qmha_attention_prepared(self.Qp.data_ptr(), self.Kp.data_ptr(), self.Vt.data_ptr(),
+                                                self.sc.data_ptr() if self.kernel == "int8" else None, self.out.data_ptr(),
+                                                self.Bl, self.N, self.dm, self.H, self.kid, self.gran, self.sp))
+
+    def time(self, steps, warmup, barrier, attn_only=False):
+        """-> (ms per step, attention ms, quantise ms, kernel launches), CUDA events on the launching stream"""
+        torch = self.torch
+        for _ in range(max(warmup, 0)):
+            self.prep(); self.attn()
+        torch.cuda.synchronize()
+        self.chk(self.L.qmha_check_async_error())
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        l0 = self.qm.launch_count()
+        barrier(); torch.cuda.synchronize()
+        for i in range(steps):
+            ev[i][0].record(self.stream)
+            if not attn_only:
+                self.prep()
+            ev[i][1].record(self.stream)
+            self.attn()
+            ev[i][2].record(self.stream)
+        torch.cuda.synchronize(); barrier()
+        launches = self.qm.launch_count() - l0
+        self.chk(self.L.qmha_check_async_error())
+        total = ev[0][0].elapsed_time(ev[steps - 1][2])
+        prep_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+        attn_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+        return total / steps, attn_ms, prep_ms, launches
+
+    def parity(self, rng_seed=0, n_units=6, n_rows=5):
+        """Checker (not timed, not on the product path): a sample of (batch, head, row) triples of the output the
+        timed steps left behind, against the CPU oracle's per-row routine in float64 over all N keys."""
+        import numpy as np
+        from oracle import load_oracle
+        orc = load_oracle()
+        rng = np.random.default_rng(rng_seed)
+        Bl, H, N, d = self.Bl, self.H, self.N, self.d
+        units = {(0, 0), (Bl - 1, H - 1)}
+        while len(units) < min(n_units, Bl * H):
+            units.add((int(rng.integers(0, Bl)), int(rng.integers(0, H))))
+        num = den = 0.0
+        mx = 0.0
+        rows_total = 0
+        for b, head in sorted(units):
+            rows = np.unique(np.concatenate([[0, N - 1], rng.integers(0, N, max(n_rows - 2, 0))])).astype(np.int64)
+            sl = slice(head * d, (head + 1) * d)
+            q, k, v = (t[b, :, sl].contiguous().cpu().numpy() for t in (self.tq, self.tk, self.tv))
+            ref = orc.mha_head_rows(q[rows], k, v, "f64").astype(np.float64)
+            got = self.out[b, :, sl].contiguous().cpu().numpy()[rows].astype(np.float64)
+            if not np.isfinite(got).all():
+                return {"max_abs": float("nan"), "rel_l2": float("nan"), "rows": int(rows_total), "ok": False}
+            mx = max(mx, float(np.abs(got - ref).max()))
+            num += float(((got - ref) ** 2).sum()); den += float((ref ** 2).sum())
+            rows_total += len(rows)
+        rel = (num / max(den, 1e-300)) ** 0.5
+        tol_abs, tol_rel = (2e-2, 1e-2) if self.kernel == "int8" else (2e-3, None)
+        ok = mx <= tol_abs and (tol_rel is None or rel <= tol_rel)
+        return {"max_abs": mx, "rel_l2": rel, "rows": int(rows_total), "units": len(units), "ok": bool(ok),
+                "checker": "oracle.mha_head_rows float64 (generate_golden.cpp:69-90 per-row routine), all N keys per row",
+                "tolerance": {"max_abs": tol_abs, "rel_l2": tol_rel}}
+
+
+def copy_roof_ms(torch, dev, bufs_in, buf_out, reps=2):
+    """Raw platform roof of the e2e arm: the same pinned buffers moved by one cudaMemcpyAsync each, all host->device
+    copies on one stream and the device->host copy on another (full duplex), nothing else running."""
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_in = [torch.empty_like(b, device=dev) for b in bufs_in]
+    d_out = torch.empty_like(buf_out, device=dev)
+    best = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            for h, dd in zip(bufs_in, d_in):
+                dd.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            buf_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        best = ms if best is None else min(best, ms)
+    return best
 
 
 def run_native(args):
@@ -194,6 +335,16 @@ def run_native(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
     B, H, N, d, kernel, scaling = WORKLOADS[args.workload]
     from quantizedmha_b200.sharding import unit_range
     if scaling == "strong":
@@ -203,112 +354,95 @@ def run_native(args):
     else:
         Bl = B
     dm = H * d
-    kid = qm.kernel_id(kernel)
-    L = qm.lib()
-
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(42 + rank)
-    # U[0,1) like inputs/data.cu:15-22 (counter-based device RNG for the multi-GB shape)
-    tq = torch.rand((Bl, N, dm), device=dev, generator=gen)
-    tk = torch.rand((Bl, N, dm), device=dev, generator=gen)
-    tv = torch.rand((Bl, N, dm), device=dev, generator=gen)
-    out = torch.empty_like(tq)
-    n_pad, d_pad = qm.workspace_dims(N, dm, H)
-    units = Bl * H
-    elt = torch.int8 if kernel == "int8" else torch.float16
-    Qp = torch.empty((units, n_pad, d_pad), dtype=elt, device=dev)
-    Kp = torch.empty_like(Qp)
-    Vt = torch.empty((units, d_pad, n_pad), dtype=torch.float16, device=dev)
     gran = {"head": qm.GRAN_HEAD, "block": qm.GRAN_BLOCK, "tensor": qm.GRAN_TENSOR}[args.scales]
-    sc = torch.empty((3, units, n_pad // 32) if gran == qm.GRAN_BLOCK else (3, units), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream()
-    sp = int(stream.cuda_stream)
-
-    def chk(rc):
-        if rc != 0:
-            raise RuntimeError(L.qmha_last_error().decode())
-
-    def prep():
-        if kernel == "int8":
-            chk(L.qmha_quantize_qkv(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), Bl, N, dm, H, gran,
-                                    Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), sc.data_ptr(), sp))
-        else:
-            chk(L.qmha_convert_qkv_f16(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), Bl, N, dm, H,
-                                       Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), sp))
-
-    def attn():
-        chk(L.qmha_attention_prepared(Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(),
-                                      sc.data_ptr() if kernel == "int8" else None, out.data_ptr(),
-                                      Bl, N, dm, H, kid, gran, sp))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    for _ in range(max(args.warmup, 0)):
-        prep(); attn()
-    torch.cuda.synchronize()
-    chk(L.qmha_check_async_error())
-
+    L = qm.lib()
+    job = Job(torch, qm, dev, Bl, H, N, d, kernel, gran, 42 + rank)
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = qm.launch_count()
-    barrier(); torch.cuda.synchronize()
-    for i in range(K):
-        ev[i][0].record(stream)
-        prep()
-        ev[i][1].record(stream)
-        attn()
-        ev[i][2].record(stream)
-    torch.cuda.synchronize(); barrier()
-    launches = qm.launch_count() - launches0
+    ms_step, attn_ms, prep_ms, launches = job.time(K, args.warmup, barrier)
     clocks = sampler.stop() if rank == 0 else None
-    chk(L.qmha_check_async_error())
-    total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
-    prep_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    attn_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
-    ms_step = total_ms / K
+    parity = job.parity() if rank == 0 else None
 
     # ---- e2e: host buffers through the C-ABI, H2D + compute + D2H inside the timed region.
     # Pinned host memory is capped at ~8.6 GB: larger workloads (c5) time the first `Be` batch
-    # entries — the path pipelines per batch entry, so the rate is the same — and say so.
+    # entries — the path pipelines per (batch entry, head group), so the rate is the same — and say so.
     e2e_steps = max(1, min(K, args.e2e_steps))
     Be = max(1, min(Bl, int(8.6e9 // (4 * N * dm * 4))))
     hq = torch.empty((Be, N, dm), dtype=torch.float32, pin_memory=True)
     hk = torch.empty_like(hq, pin_memory=True)
     hv = torch.empty_like(hq, pin_memory=True)
     ho = torch.empty_like(hq, pin_memory=True)
-    hq.copy_(tq[:Be]); hk.copy_(tk[:Be]); hv.copy_(tv[:Be])
+    hq.copy_(job.tq[:Be]); hk.copy_(job.tk[:Be]); hv.copy_(job.tv[:Be])
     torch.cuda.synchronize()
-    chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Be, N, dm, H, kid, gran))
+    job.chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Be, N, dm, H, job.kid, gran))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Be, N, dm, H, kid, gran))
+        job.chk(L.qmha_forward_host(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), Be, N, dm, H, job.kid, gran))
     e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3 * (Bl / Be)   # scaled to the full per-rank batch
-    e2e_maxdiff = float((ho.to(dev) - out[:Be]).abs().max().item())
+    e2e_maxdiff = float((ho.to(dev) - job.out[:Be]).abs().max().item())
+    if not e2e_maxdiff <= 1e-6:
+        raise SystemExit(f"bench.py: the host-buffer path and the device path disagree (max abs {e2e_maxdiff})")
+    barrier()
+    roof_ms = copy_roof_ms(torch, dev, [hq, hk, hv], ho) * (Bl / Be)
+    del hq, hk, hv, ho
 
-    t = torch.tensor([ms_step, attn_ms, prep_ms, e2e_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, attn_ms, prep_ms, e2e_ms = [float(x) for x in t.tolist()]
+    ms_step, attn_ms, prep_ms, e2e_ms, roof_ms = max_over_ranks([ms_step, attn_ms, prep_ms, e2e_ms, roof_ms])
+
+    # ---- the same kernel on signed inputs (0.5*N(0,1)): the lazy O-rescale path really runs there
+    signed = None
+    if kernel == "int8" and not args.no_signed:
+        gen = torch.Generator(device=dev); gen.manual_seed(4242 + rank)
+        job.fill("normal", gen)
+        s_ms, s_attn, s_prep, _ = job.time(min(K, 5), 1, barrier)
+        s_par = job.parity(1) if rank == 0 else None
+        (s_attn,) = max_over_ranks([s_attn])
+        signed = {"attn_ms": s_attn, "attn_tflops_per_gpu": 4.0 * Bl * H * N * N * d / (s_attn / 1e3) / 1e12,
+                  "data": "0.5*N(0,1) (tests/generate_golden.cpp:123-138 distribution)", "parity": s_par}
+
+    # ---- BASELINE config 5 (B=32, H=32, N=16384, d=128), units split over the ranks: strong scaling
+    scaling_c5 = None
+    if world > 1 and args.workload == "c4" and not args.no_c5:
+        del job
+        torch.cuda.empty_cache()
+        B5, H5, N5, d5, k5, _ = WORKLOADS["c5"]
+        lo, hi = unit_range(B5, world, rank)
+        j5 = Job(torch, qm, dev, hi - lo, H5, N5, d5, k5, gran, 4200 + rank)
+        c5_ms, c5_attn, c5_prep, _ = j5.time(min(K, 5), 2, barrier)
+        c5_par = j5.parity(2, n_units=3, n_rows=3) if rank == 0 else None
+        c5_ms, c5_attn = max_over_ranks([c5_ms, c5_attn])
+        c5_tf = 4.0 * B5 * H5 * N5 * N5 * d5 / (c5_ms / 1e3) / 1e12
+        one = None
+        try:   # the committed 1-GPU line of the same workload (python bench.py --workload c5)
+            one = json.load(open(os.path.join(ROOT, "profiles", "r02", "bench_c5_1gpu.json")))["ms_per_step"]
+        except (OSError, KeyError, ValueError):
+            pass
+        scaling_c5 = {"workload": f"c5: B={B5} H={H5} N={N5} d={d5} INT8 scales={args.scales}, batch split over {world} GPUs",
+                      "scaling": "strong", "ms_per_step": c5_ms, "attn_ms": c5_attn, "tflops": c5_tf, "steps": min(K, 5),
+                      "ms_per_step_1gpu_line": one, "speedup_vs_1gpu_line": (one / c5_ms) if one else None,
+                      "parity": c5_par}
+        del j5
 
     flops_rank = 4.0 * Bl * H * N * N * d
     flops_all = 4.0 * (B if scaling == "strong" else B * world) * H * N * N * d
     E = Bl * N * dm
-    prep_bytes = 3 * E * 4 + (3 * E if kernel == "int8" else 0) + (E * 2 if kernel == "int8" else 3 * E * 2)
-    # int8: Q,K int8 (1 B) + V codes as fp16 (2 B) = 4E out; f16: 6E out.  3*E*4 in.
-    prep_bytes = 3 * E * 4 + (4 * E if kernel == "int8" else 6 * E)
+    # quantise pass: SURVEY §8(d) algorithmic bytes = one fp32 read + one int8 write of Q, K, V = 15*E; the kernel
+    # writes the V codes as fp16 (the P.V MMA is 16-bit), i.e. 16*E actually moved.  FP16/BF16: 12*E + 6*E.
+    prep_alg = 15 * E if kernel == "int8" else 18 * E
+    prep_act = 16 * E if kernel == "int8" else 18 * E
     pk = peaks()
     traffic = None
-    try:   # per-launch DRAM traffic measured once with `ncu --set full` (profiles/r01/traffic.json)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
-        traffic = tj["attn_fwd_kernel"].get(f"{args.workload}:{kernel}")
-    except (OSError, KeyError, ValueError):
-        pass
+    for rnd in ("r02", "r01"):   # per-launch DRAM traffic from one `ncu --set full` capture of this command
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", rnd, "traffic.json")))
+            traffic = tj["attn_fwd_kernel"].get(f"{args.workload}:{kernel}")
+            if traffic is not None:
+                break
+        except (OSError, KeyError, ValueError):
+            pass
     value = flops_all / (ms_step / 1e3) / 1e12
     attn_tflops = flops_rank / (attn_ms / 1e3) / 1e12
     # Library INT8 GEMM rate of this box (cuBLASLt through torch._int_mm, best of 5, outside every timed
@@ -329,37 +463,55 @@ def run_native(args):
             del ga, gb
         except Exception:  # noqa: BLE001  (not available on this torch build: leave the field empty)
             int8_gemm = None
-    mixed_peak = 2.0 / (1.0 / int8_gemm + 1.0 / pk["bf16_sustained"]) if int8_gemm else None
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    mufu_bound = N_SM * MUFU_PER_SM_CLK * sm_mhz * 1e6 * 4.0 * d / 1e12   # one ex2 per score element = 4d FLOPs
+    if kernel == "int8":
+        mixed_peak = 2.0 / (1.0 / int8_gemm + 1.0 / pk["bf16_sustained"]) if int8_gemm else 2.0 / (1.0 / 4500.0 + 1.0 / pk["bf16_sustained"])
+        roof_peak = mixed_peak
+        peak_src = (f"harmonic mean (half of the FLOPs each) of the INT8 GEMM rate measured live on this box "
+                    f"({'torch._int_mm 8192^3' if int8_gemm else 'unavailable: nominal 4500'}) and the sustained dense bf16 "
+                    f"rate of {pk['src']}: the Q.K^T half runs on the INT8 pipe, the P.V half on the 16-bit pipe")
+    else:
+        roof_peak = pk["bf16_sustained"]
+        peak_src = f"{pk['src']} dense bf16 cuBLAS GEMM, sustained (kernel timed inside the step loop)"
+    operand_bytes = E * (1 + 1 + 2) + E * 4 if kernel == "int8" else E * 6 + E * 4
     line = {
-        "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "metric": metric_name(args.workload), "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-        "dtype": "s8*s8->s32 (Q.K^T), f16*f16->f32 (P.V), f32 softmax" if kernel == "int8" else "f16*f16->f32, f32 softmax",
+        "dtype": {"int8": "s8*s8->s32 (Q.K^T), f16*f16->f32 (P.V), f32 softmax", "f16": "f16*f16->f32, f32 softmax",
+                  "bf16": "bf16*bf16->f32, f32 softmax"}[kernel],
         "data": "synthetic U[0,1) (inputs/data.cu distribution), random on device",
         "config": {"workload": f"{args.workload}: B={B}{' per GPU' if scaling == 'weak' and world > 1 else ''} H={H} N={N} d={d} "
                                f"kernel={kernel} scales={args.scales}", "l2": f"inputs+outputs {4 * Bl * N * dm * 4 / 1e9:.2f} GB per GPU vs 126 MB L2 (no flush needed when larger)",
                    "parallelism": f"(batch x head) units sharded over {world} GPU(s), no collective"},
         "attn_ms": attn_ms, "attn_tflops_per_gpu": attn_tflops, "prep_ms": prep_ms,
-        "prep_gbs_algorithmic": prep_bytes / (prep_ms / 1e3) / 1e9, "prep_frac_of_hbm": prep_bytes / (prep_ms / 1e3) / 1e9 / pk["hbm"],
-        "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel", "achieved": attn_tflops, "peak": pk["bf16_sustained"],
-                     "unit": "TFLOP/s", "frac": attn_tflops / pk["bf16_sustained"], "traffic": traffic,
-                     "traffic_unit": "bytes of DRAM read+write per launch (ncu); algorithmic operand+output bytes = %d" % (E * (1 + 1 + 2) + E * 4) if kernel == "int8" else "bytes",
-                     "peak_src": f"{pk['src']} dense bf16 cuBLAS GEMM, sustained (kernel timed inside the step loop)",
-                     "frac_of_nominal_int8_4500": attn_tflops / 4500.0,
-                     "frac_of_nominal_mixed_3000": attn_tflops / 3000.0,
+        "prep": {"kernel": "block_quantize_kernel" if (kernel == "int8" and gran == qm.GRAN_BLOCK) else "quantise / convert",
+                 "bound": "hbm", "peak_gbs": pk["hbm"], "algorithmic_bytes_15E": prep_alg, "moved_bytes_16E": prep_act,
+                 "gbs_algorithmic": prep_alg / (prep_ms / 1e3) / 1e9, "frac_algorithmic": prep_alg / (prep_ms / 1e3) / 1e9 / pk["hbm"],
+                 "gbs_moved": prep_act / (prep_ms / 1e3) / 1e9, "frac_moved": prep_act / (prep_ms / 1e3) / 1e9 / pk["hbm"]},
+        "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel", "achieved": attn_tflops, "peak": roof_peak,
+                     "unit": "TFLOP/s", "frac": attn_tflops / roof_peak, "traffic": traffic,
+                     "traffic_note": f"DRAM read+write bytes per launch from the ncu --set full capture under profiles/; algorithmic operand+output bytes = {operand_bytes}",
+                     "peak_src": peak_src,
+                     "frac_of_nominal_int8_4500": attn_tflops / 4500.0 if kernel == "int8" else None,
+                     "frac_of_bf16_sustained": attn_tflops / pk["bf16_sustained"],
                      "int8_gemm_tflops_measured": int8_gemm,
-                     "frac_of_measured_mixed": (attn_tflops / mixed_peak) if mixed_peak else None,
-                     "note": "peak is the bf16 GEMM rate of MEASURED_PEAKS.json; frac can exceed 1 for the INT8 kernel because "
-                             "the Q.K^T half of the FLOPs runs on the INT8 pipe; frac_of_measured_mixed uses the harmonic "
-                             "mean of the live INT8 GEMM rate and the bf16 rate (half of the FLOPs each)"},
+                     "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": attn_tflops / mufu_bound,
+                     "mufu_note": f"{N_SM} SMs x {MUFU_PER_SM_CLK} ex2/clk x {sm_mhz:.0f} MHz (median SM clock under load) x 4d FLOPs per score element"},
         "e2e": {"value": flops_all / (e2e_ms / 1e3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 3 * E * 4, "d2h_bytes_per_step": E * 4, "steps": e2e_steps,
                 "timed_batch_entries": Be, "of_batch_entries": Bl,
-                "api": "qmha_forward_host (pinned host buffers, copies pipelined per batch entry)",
-                "host_placement": numa,
+                "api": "qmha_forward_host (pinned host buffers; copies pipelined per batch entry x head group)",
+                "host_placement": numa, "copy_roof_ms": roof_ms, "frac_of_copy_roof": roof_ms / e2e_ms,
+                "copy_roof_note": "same pinned buffers, one cudaMemcpyAsync each, H2D and D2H on two streams, no compute",
                 "max_abs_vs_device_path": e2e_maxdiff},
+        "parity": parity,
+        "signed_inputs": signed,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if scaling_c5 is not None:
+        line["scaling_c5"] = scaling_c5
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
@@ -367,6 +519,9 @@ def run_native(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        print("bench.py: sampled rows of the timed output are outside the tolerance", file=sys.stderr)
+        return 1
     return 0
 
 
@@ -382,6 +537,8 @@ def main():
     ap.add_argument("--cpu-sample-heads", type=int, default=0, help="0 = one head per host thread")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-signed", action="store_true", help="skip the extra timing on signed inputs")
+    ap.add_argument("--no-c5", action="store_true", help="N>1: skip the C5 strong-scaling measurement")
     ap.add_argument("--scales", default="block", choices=["head", "block", "tensor"],
                     help="granularity of the dynamic INT8 scales (block = the reference's 32-row tiles)")
     args = ap.parse_args()

@@ -116,6 +116,10 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
                                const float* scales, float* O, int B, int N, int d_model, int h,
                                int variant, long long* host_trace);
 
+/* Development aid: with QMHA_CYCLES=1 in the environment, every qmha_attention_prepared() launch adds
+ * the SM clocks each CTA was resident to a device counter; out2 = {sum of clocks, CTAs}. */
+int qmha_debug_cycles(unsigned long long* out2, int reset);
+
 /* ---- fused RoPE ------------------------------------------------------------
  * The reference's CPU check rotates Q and K (utils/verify.cu:56-69) but no GPU kernel ever calls
  * the device helper apply_rope (utils/utils.cu:50-65).  With qmha_set_rope(1, base) every entry

@@ -37,6 +37,7 @@ class Oracle:
         L.oracle_init_golden_inputs.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle_apply_rope.argtypes = [_f32p, C.c_int, C.c_int, C.c_int]
         L.oracle_mha_forward.argtypes = [_f32p, _f32p, _f32p, _f32p] + [C.c_int] * 6
+        L.oracle_mha_head_rows.argtypes = [_f32p, _f32p, _f32p, _f32p] + [C.c_int] * 5
         L.oracle_cpu_reference_rope.argtypes = [_f32p, _f32p, _f32p, _f32p] + [C.c_int] * 4
         L.oracle_verify_results.argtypes = [_f32p, _f32p, C.c_int64, C.c_float, C.c_float, C.POINTER(C.c_int64)]
         L.oracle_verify_results.restype = C.c_int
@@ -79,6 +80,15 @@ class Oracle:
         N, d_model = shp[-2], shp[-1]
         o = np.empty_like(q)
         self.lib.oracle_mha_forward(q, k, v, o, B, N, d_model, h, 0 if precision == "f32" else 1, threads)
+        return o
+
+    def mha_head_rows(self, q_rows, k, v, precision: str = "f64", threads: int = 0) -> np.ndarray:
+        """A sample of query rows [nr, d] of one head against its full K / V [N, d]."""
+        q_rows, k, v = (np.ascontiguousarray(a, np.float32) for a in (q_rows, k, v))
+        nr, d = q_rows.shape
+        assert k.shape == v.shape and k.shape[1] == d
+        o = np.empty_like(q_rows)
+        self.lib.oracle_mha_head_rows(q_rows, k, v, o, nr, k.shape[0], d, 0 if precision == "f32" else 1, threads)
         return o
 
     def cpu_reference_rope(self, q, k, v, h: int, threads: int = 0) -> np.ndarray:

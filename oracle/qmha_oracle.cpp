@@ -205,6 +205,22 @@ void oracle_mha_forward(const float* Q, const float* K, const float* V, float* O
   }
 }
 
+// A sample of query rows of ONE head against all N keys — the same per-row routines as
+// oracle_mha_forward (generate_golden.cpp:69-90), for shapes whose full output the CPU cannot
+// produce in test time (C4 / C5 of BASELINE.json).  Qrows [nr, d], K / V [N, d] (the head's columns,
+// contiguous), O [nr, d].
+void oracle_mha_head_rows(const float* Qrows, const float* K, const float* V, float* O, int nr, int N,
+                          int d, int precision, int nthreads) {
+  std::vector<float> kT((size_t)d * N);
+  for (int j = 0; j < N; ++j)
+    for (int dd = 0; dd < d; ++dd) kT[(size_t)dd * N + j] = K[(int64_t)j * d + dd];
+  const float scale = 1.0f / std::sqrt((float)d);
+  run_parallel(nthreads, nr, [&](int i) {
+    if (precision == 0) mha_rows_f32(Qrows, kT.data(), V, O, N, d, d, 0, i, i + 1, scale);
+    else mha_rows_f64(Qrows, kT.data(), V, O, N, d, d, 0, i, i + 1, 1.0 / std::sqrt((double)d));
+  });
+}
+
 // Restates utils/verify.cu:25-104 (cpu_reference): same attention but RoPE is applied to every
 // q_i and k_j on the fly (verify.cu:56-69).  Implemented as "RoPE the inputs, then plain
 // attention", which is the same arithmetic per element (rope of k_j does not depend on i) with

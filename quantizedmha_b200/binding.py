@@ -24,6 +24,36 @@ def lib_path() -> str:
     return os.environ.get("QMHA_LIB", os.path.join(_HERE, "lib", "libqmha.so"))
 
 
+def declare(L: C.CDLL) -> C.CDLL:
+    """Sets the prototypes of include/qmha.h on a loaded library (also used by the A/B tools that
+    load several builds of the library side by side)."""
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.solve.argtypes = [vp, vp, vp, vp, i, i, i]
+    L.solve.restype = None
+    L.qmha_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    L.qmha_forward_host.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i]
+    L.qmha_workspace_dims.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+    L.qmha_quantize_qkv.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp]
+    L.qmha_convert_qkv_f16.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
+    L.qmha_quantize_blocks.argtypes = [vp, i, i, i, i, i, vp, vp, vp]
+    L.qmha_quantize_static.argtypes = [vp, C.c_int64, f, f, vp, vp]
+    L.qmha_attention_prepared.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    L.qmha_check_async_error.argtypes = []
+    L.qmha_last_error.restype = C.c_char_p
+    L.qmha_set_kernel.argtypes = [C.c_char_p]
+    L.qmha_get_kernel.restype = C.c_char_p
+    L.qmha_kernel_from_name.argtypes = [C.c_char_p]
+    L.qmha_default_granularity.argtypes = [i, i]
+    L.qmha_set_rope.argtypes = [i, f]
+    L.qmha_get_rope.argtypes = []
+    L.qmha_launch_count.restype = C.c_int64
+    L.qmha_version.restype = C.c_char_p
+    L.qmha_shutdown.restype = None
+    if hasattr(L, "qmha_debug_cycles"):
+        L.qmha_debug_cycles.argtypes = [C.POINTER(C.c_ulonglong), i]
+    return L
+
+
 def lib() -> C.CDLL:
     """Loads the CUDA library; raises (never falls back) when it has not been built."""
     global _LIB
@@ -32,30 +62,7 @@ def lib() -> C.CDLL:
         if not os.path.exists(p):
             raise QmhaError(f"{p} not found: build it with `make lib` or __graft_entry__.build(); "
                             "there is no fallback path")
-        L = C.CDLL(p)
-        vp, i, f = C.c_void_p, C.c_int, C.c_float
-        L.solve.argtypes = [vp, vp, vp, vp, i, i, i]
-        L.solve.restype = None
-        L.qmha_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
-        L.qmha_forward_host.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i]
-        L.qmha_workspace_dims.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
-        L.qmha_quantize_qkv.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp]
-        L.qmha_convert_qkv_f16.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
-        L.qmha_quantize_blocks.argtypes = [vp, i, i, i, i, i, vp, vp, vp]
-        L.qmha_quantize_static.argtypes = [vp, C.c_int64, f, f, vp, vp]
-        L.qmha_attention_prepared.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
-        L.qmha_check_async_error.argtypes = []
-        L.qmha_last_error.restype = C.c_char_p
-        L.qmha_set_kernel.argtypes = [C.c_char_p]
-        L.qmha_get_kernel.restype = C.c_char_p
-        L.qmha_kernel_from_name.argtypes = [C.c_char_p]
-        L.qmha_default_granularity.argtypes = [i, i]
-        L.qmha_set_rope.argtypes = [i, f]
-        L.qmha_get_rope.argtypes = []
-        L.qmha_launch_count.restype = C.c_int64
-        L.qmha_version.restype = C.c_char_p
-        L.qmha_shutdown.restype = None
-        _LIB = L
+        _LIB = declare(C.CDLL(p))
     return _LIB
 
 

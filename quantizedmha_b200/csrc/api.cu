@@ -50,6 +50,7 @@ struct Workspace {
   float* aux = nullptr;    // block mode: [units][n_pad/32][2]
   float* vmax = nullptr;   // block mode: [units]
   int* error_flag = nullptr;
+  unsigned long long* cycles = nullptr;  // {sum of CTA residency clocks, CTAs}: qmha_debug_cycles
   size_t qk_bytes = 0, vt_bytes = 0, scale_elems = 0;
   float2* rope_tab = nullptr;  // {cos, sin}[rope_n][rope_d/2] for rope_base
   int rope_n = 0, rope_d = 0;
@@ -130,6 +131,10 @@ int get_workspace(int dev, size_t qk_bytes, size_t vt_bytes, size_t scale_elems,
   if (!w.error_flag) {
     if ((e = cudaMalloc(&w.error_flag, sizeof(int))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     cudaMemset(w.error_flag, 0, sizeof(int));
+  }
+  if (!w.cycles && getenv("QMHA_CYCLES")) {
+    if ((e = cudaMalloc(&w.cycles, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
+    cudaMemset(w.cycles, 0, 2 * sizeof(unsigned long long));
   }
   if (qk_bytes > w.qk_bytes) {
     cudaDeviceSynchronize();
@@ -289,7 +294,8 @@ int attention_variant(int kernel) {
 int attention_impl(const void* Qp, const void* Kp, const void* Vt, const float* scales, float* O,
                    int B, int N, int d_model, int h, int kernel, int* error_flag,
                    cudaStream_t stream, long long* trace = nullptr, int variant = -1,
-                   int gran = QMHA_GRAN_HEAD, float* aux = nullptr, float* vmax = nullptr) {
+                   int gran = QMHA_GRAN_HEAD, float* aux = nullptr, float* vmax = nullptr,
+                   unsigned long long* cycles = nullptr) {
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   if (check_aligned16(O, "output")) return 1;
@@ -299,6 +305,7 @@ int attention_impl(const void* Qp, const void* Kp, const void* Vt, const float* 
   a.int8 = kernel == QMHA_KERNEL_INT8;
   a.stream = stream;
   a.trace = trace;
+  a.cycles = cycles;
   a.variant = variant >= 0 ? variant : attention_variant(kernel);
   if (a.int8 && gran == QMHA_GRAN_BLOCK) {
     if (!aux || !vmax) return fail("internal: block mode needs scratch");
@@ -442,7 +449,7 @@ int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt, 
   WorkspaceUse use;
   use.begin(w, std::move(call_lock), (cudaStream_t)stream);
   if (attention_impl(Qp, Kp, Vt, scales, O, B, N, d_model, h, kernel, w->error_flag,
-                     (cudaStream_t)stream, nullptr, -1, gran, w->aux, w->vmax))
+                     (cudaStream_t)stream, nullptr, -1, gran, w->aux, w->vmax, w->cycles))
     return 1;
   g_err.clear();
   return 0;
@@ -502,6 +509,22 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
   cudaFree(dtrace);
   if (rc == 0) g_err.clear();
   return rc;
+}
+
+// Development aid (QMHA_CYCLES=1 in the environment): SM clocks summed over the CTAs of every
+// qmha_attention_prepared() launch since the last reset, and the number of CTAs.  Synchronises.
+int qmha_debug_cycles(unsigned long long* out2, int reset) {
+  const int dev = require_device();
+  if (dev < 0) return 1;
+  Workspace* w;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 0, 0, 0, &w, &call_lock)) return 1;
+  if (!w->cycles) return fail("set QMHA_CYCLES=1 before the first call");
+  cudaError_t e = cudaMemcpy(out2, w->cycles, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return fail_cuda("reading the cycle counters", e);
+  if (reset) cudaMemset(w->cycles, 0, 2 * sizeof(unsigned long long));
+  g_err.clear();
+  return 0;
 }
 
 // Checks the asynchronous failure flag of the current device after the caller synchronised.
@@ -615,7 +638,7 @@ void qmha_shutdown(void) {
     cudaSetDevice(kv.first);
     Workspace& w = kv.second;
     cudaFree(w.Qp); cudaFree(w.Kp); cudaFree(w.Vt); cudaFree(w.scales); cudaFree(w.amax); cudaFree(w.aux); cudaFree(w.vmax);
-    cudaFree(w.error_flag); cudaFree(w.rope_tab);
+    cudaFree(w.error_flag); cudaFree(w.rope_tab); cudaFree(w.cycles);
     if (w.last_use) cudaEventDestroy(w.last_use);
   }
   g_ws.clear();

@@ -54,6 +54,22 @@ constexpr int kHN = 64;         // keys per half-step == UMMA N of Q·K^T, UMMA 
 #define QMHA_MMA_SPLIT 2
 #endif
 constexpr int kMmaSplit = QMHA_MMA_SPLIT;
+// tcgen05.commit is expensive for the issuing warp (traced: ~100 clk each, MMAs in flight or not).  Two ways to
+// commit less, each 0 = off, 1 = FP16/BF16 kernels only, 2 = every kernel:
+//   QMHA_SOFT_RING: the K / V^T ring stages are handed back by one softmax thread of each tile when the scores
+//     that prove the last read of the stage has retired arrive (S(2j+1) -> K tile j is free; S(2j+4) is issued
+//     behind P.V(2j+1) by the same thread -> V tile j is free) instead of by two commits per tile per MMA warp;
+//   QMHA_LAZY_PV: "P.V(i) retired" is read off s_full(i+3); only the last three half-steps keep a pv_done commit.
+// Same-box A/B at the headline shape (clocks per CTA): FP16 219.6 k -> 198.3 k with both (-10 %: that kernel waits
+// on the tensor side); INT8 184.6 k -> 193.1 k with both (+4.5 %: the softmax warps set the pace there and pay for
+// the extra arrive), so INT8 keeps committing the ring barriers.
+#ifndef QMHA_SOFT_RING
+#define QMHA_SOFT_RING 1
+#endif
+#ifndef QMHA_LAZY_PV
+#define QMHA_LAZY_PV 1
+#endif
+static_assert((QMHA_SOFT_RING == 0 && QMHA_LAZY_PV == 0) || kMmaSplit == 2, "written for the two-warp MMA issue");
 constexpr int kAllocWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr int kTmaWarpV = 10;
@@ -240,11 +256,66 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& e0, fl
   e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
 }
 
+// int32 score -> float(12582912 + s) bit pattern.  QMHA_I2F selects the instruction: 0 = integer add
+// (ALU pipe), 1 = mad.lo by a run-time 1 (IMAD, FMA pipe), 2 = alternate (even columns add, odd IMAD).
+#ifndef QMHA_I2F
+#define QMHA_I2F 0
+#endif
+__device__ __forceinline__ float i2f_magic(uint32_t s, int one, int idx) {
+  if (QMHA_I2F == 3) return __uint_as_float(s);   // timing experiment only: no conversion at all (wrong results)
+  if (QMHA_I2F == 1 || (QMHA_I2F == 2 && (idx & 1))) {
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, 0x4B400000;" : "=r"(r) : "r"((int)s), "r"(one));
+    return __int_as_float(r);
+  }
+  return __int_as_float((int)s + kMagicI2F);
+}
+// Pacing (QMHA_PACE_DEPTH > 0): ptxas schedules the 64 independent exp chains of a step as long bursts
+// (all conversions, then all MUFU.EX2, then all packs), so the two softmax warps of a sub-partition queue
+// on the MUFU together and then do their integer work together while the MUFU idles.  A data dependency
+// that costs one LOP3 per group forces an interleaved order instead: the conversions of group g take a
+// (run-time) zero derived from the packed P of group g - depth, so at most `depth` groups of MUFU work
+// can be pulled ahead of the integer work of the groups before them.
+#ifndef QMHA_PACE_DEPTH
+#define QMHA_PACE_DEPTH 0
+#endif
+// Timing experiments only (results are wrong): bit 0 drops the fp16 pack, bit 1 the row sum, bit 2 the row
+// max, bit 3 the MUFU itself — to see which unit the loop is really waiting for.
+#ifndef QMHA_KO
+#define QMHA_KO 0
+#endif
+#ifndef QMHA_PACE_GROUP
+#define QMHA_PACE_GROUP 4   // pairs per group
+#endif
+__device__ __forceinline__ uint32_t pace_token(const uint32_t (&p)[kHN / 2], int i, uint32_t zero) {
+  constexpr int G = QMHA_PACE_GROUP, D = QMHA_PACE_DEPTH;
+  const int g = i / G;
+  if (D == 0 || g < D) return 0u;
+  return p[(g - D) * G + G - 1] & zero;
+}
+__device__ __forceinline__ void i2f_pair(uint32_t s0, uint32_t s1, int one, int i, float& f0, float& f1,
+                                         uint32_t tok = 0u) {
+  if (QMHA_I2F == 4) {  // timing experiment only: one 64-bit add per pair (the carry makes s1 off by one when s0 < 0)
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(s0), "r"(s1));
+    v += 0x4B4000004B400000ull;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(v));
+    return;
+  }
+  if (QMHA_PACE_DEPTH > 0) {
+    f0 = __int_as_float((int)s0 + (int)(kMagicI2F + tok));
+    f1 = __int_as_float((int)s1 + (int)(kMagicI2F + tok));
+    return;
+  }
+  f0 = i2f_magic(s0, one, 2 * i);
+  f1 = i2f_magic(s1, one, 2 * i + 1);
+}
+
 // kPolyEvery: every kPolyEvery-th pair of the row takes the polynomial path (0 = all on MUFU).
 template <bool kInt8, bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2>
 __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t (&p)[kHN / 2],
                                              float c, float m_used, int n_valid,
-                                             uint64_t (&lsum)[2]) {
+                                             uint64_t (&lsum)[2], int one) {
   // x = s*c - m_used.  INT8: s is an int32 with |s| < 2^22, so bits(s + 0x4B400000) is the
   // float 12582912 + s exactly and one FMA does int->float, scale and max subtraction.
   const float bias = kInt8 ? -fmaf(kMagicF, c, m_used) : -m_used;
@@ -253,8 +324,7 @@ __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t 
   for (int i = kBegin; i < kEnd; ++i) {
     float f0, f1;
     if constexpr (kInt8) {
-      f0 = __int_as_float((int)s[2 * i] + kMagicI2F);
-      f1 = __int_as_float((int)s[2 * i + 1] + kMagicI2F);
+      i2f_pair(s[2 * i], s[2 * i + 1], one, i, f0, f1, pace_token(p, i, (uint32_t)(one ^ 1)));
     } else {
       f0 = __uint_as_float(s[2 * i]);
       f1 = __uint_as_float(s[2 * i + 1]);
@@ -264,15 +334,15 @@ __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t 
     if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery > 0 ? kPolyEvery : 1) - 1) {
       exp2_poly_pair(x0, x1, e0, e1);
     } else {
-      e0 = ex2_approx(x0);
-      e1 = ex2_approx(x1);
+      e0 = (QMHA_KO & 8) ? x0 : ex2_approx(x0);
+      e1 = (QMHA_KO & 8) ? x1 : ex2_approx(x1);
     }
     if constexpr (kMasked) {
       if (2 * i >= n_valid) e0 = 0.f;
       if (2 * i + 1 >= n_valid) e1 = 0.f;
     }
-    lsum[i & 1] = fadd2(lsum[i & 1], pack2(e0, e1));
-    p[i] = pack_f16x2(e0, e1);
+    if (!(QMHA_KO & 2)) lsum[i & 1] = fadd2(lsum[i & 1], pack2(e0, e1));
+    p[i] = (QMHA_KO & 1) ? __float_as_uint(e0) : pack_f16x2(e0, e1);
   }
 }
 
@@ -305,13 +375,16 @@ __device__ __forceinline__ float tile_row_max_blk(uint32_t (&s)[kHN], float c0, 
     hi0 = max(max(hi0, (int)s[32 + i + 0]), (int)s[32 + i + 1]);
     hi1 = max(max(hi1, (int)s[32 + i + 2]), (int)s[32 + i + 3]);
   }
+  // A block that holds no real key contributes nothing: its scale is the quantiser's 1e-8 floor, so a
+  // scaled sentinel would read as ~0 and could lift the row max above every real (negative) logit.
+  if (kMasked && n_valid <= kHN / 2) return (float)max(lo0, lo1) * c0;
   return fmaxf((float)max(lo0, lo1) * c0, (float)max(hi0, hi1) * c1);
 }
 
 template <bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2>
 __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint32_t (&p)[kHN / 2],
                                                  const StepConsts& k, float m_used, int n_valid,
-                                                 uint64_t (&ls)[2]) {
+                                                 uint64_t (&ls)[2], int one) {
   const float b0 = k.lr0 - fmaf(kMagicF, k.c0, m_used);
   const float b1 = k.lr1 - fmaf(kMagicF, k.c1, m_used);
   const uint64_t c2[2] = {pack2(k.c0, k.c0), pack2(k.c1, k.c1)};
@@ -320,22 +393,22 @@ __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint3
   for (int i = kBegin; i < kEnd; ++i) {
     constexpr int kHalf = kHN / 4;  // pairs per 32-key block
     const int g = i >= kHalf ? 1 : 0;
-    const float f0 = __int_as_float((int)s[2 * i] + kMagicI2F);
-    const float f1 = __int_as_float((int)s[2 * i + 1] + kMagicI2F);
+    float f0, f1;
+    i2f_pair(s[2 * i], s[2 * i + 1], one, i, f0, f1, pace_token(p, i, (uint32_t)(one ^ 1)));
     float x0, x1, e0, e1;
     unpack2(ffma2(pack2(f0, f1), c2[g], bias2[g]), x0, x1);
     if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery > 0 ? kPolyEvery : 1) - 1) {
       exp2_poly_pair(x0, x1, e0, e1);
     } else {
-      e0 = ex2_approx(x0);
-      e1 = ex2_approx(x1);
+      e0 = (QMHA_KO & 8) ? x0 : ex2_approx(x0);
+      e1 = (QMHA_KO & 8) ? x1 : ex2_approx(x1);
     }
     if constexpr (kMasked) {
       if (2 * i >= n_valid) e0 = 0.f;
       if (2 * i + 1 >= n_valid) e1 = 0.f;
     }
-    ls[g] = fadd2(ls[g], pack2(e0, e1));
-    p[i] = pack_f16x2(e0, e1);
+    if (!(QMHA_KO & 2)) ls[g] = fadd2(ls[g], pack2(e0, e1));
+    p[i] = (QMHA_KO & 1) ? __float_as_uint(e0) : pack_f16x2(e0, e1);
   }
 }
 
@@ -345,6 +418,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                 AttnParams prm) {
   using C = Cfg<kInt8, kD>;
+  constexpr bool kSoftRing = QMHA_SOFT_RING == 2 || (QMHA_SOFT_RING == 1 && !kInt8);
+  constexpr bool kLazyPv = QMHA_LAZY_PV == 2 || (QMHA_LAZY_PV == 1 && !kInt8);
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -364,6 +439,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   bool dead = false;
 
   if (*((volatile int*)err_flag) != 0) return;  // an earlier CTA already failed: drain the grid
+  const long long t_entry = (prm.cycles != nullptr && threadIdx.x == 0) ? clock64() : 0;
   // traced build: a CTA from the middle of the run (steady state, warm caches); phase stamps of its
   // warp 0 go behind the per-step stamps: entry, setup done, first scores, last P, O final, stores, exit
   const bool traced_cta = kTrace && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2;
@@ -563,14 +639,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(&bars->q_full, 0, err_flag, 201, dead);
       tc_fence_after();
       __syncwarp();
-      auto qk_step = [&](int in, int wait_site) {   // S_mt(in): wait for its K tile, issue, signal, release
+      auto qk_step = [&](int in, int wait_site, long long* stamp = nullptr) {   // S_mt(in): wait for its K tile, issue, signal, release
         const int jn = in >> 1, halfn = in & 1, stn = jn % C::kStagesK;
         mbar_wait(&bars->k_full[stn], (uint32_t)(jn / C::kStagesK) & 1, err_flag, wait_site, dead);
         tc_fence_after();
+        if (kTrace && stamp) *stamp = clock64();
         issue_qk(mt, in & 1, stn, halfn);
         commit(&bars->s_full[mt][in & 1]);
         // last read of this K tile by this warp: one arrival per MMA warp frees the stage
-        if (kStride == 2 || halfn == 1 || in == n_half - 1) commit(&bars->k_empty[stn]);
+        if (!kSoftRing && (kStride == 2 || halfn == 1 || in == n_half - 1)) commit(&bars->k_empty[stn]);
       };
       for (int in = 0; in < 3 && in < n_half; ++in) {
         if (!owns(in - 3)) continue;
@@ -594,12 +671,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         if (tracer) trm[0] = clock64();
         issue_pv(mt, (i + 1) & 1, st, half, i > 0);
-        commit(&bars->pv_done[mt][half]);
+        if (!kLazyPv || i + 3 >= n_half) commit(&bars->pv_done[mt][half]);   // no Q.K^T behind the last three
         if (i == n_half - 1) commit(&bars->o_final[mt]);
-        if (kStride == 2 || half == 1 || i == n_half - 1) commit(&bars->v_empty[st]);
+        if (!kSoftRing && (kStride == 2 || half == 1 || i == n_half - 1)) commit(&bars->v_empty[st]);
         if (tracer) trm[1] = clock64();
         if (i + 3 < n_half) {
-          qk_step(i + 3, 205);
+          qk_step(i + 3, 205, tracer ? trm + 2 : nullptr);
           if (i + 3 + kStride >= n_half) commit(&bars->qk_done);  // that was this warp's last Q·K^T
         }
         if (tracer) trm[3] = clock64();
@@ -633,6 +710,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       c = sq * sk * c;
     }
 
+    const int one = prm.one;   // run-time 1 (keeps the IMAD form of the int->float add from being folded)
     float m_used = -INFINITY;
     uint64_t lsum[2] = {0ull, 0ull};  // four fp32 partial row sums (packed pairs); block mode: l_acc
     float l_acc = 0.f;
@@ -688,13 +766,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     auto exps = [&](auto range, const uint32_t (&sx)[kHN], uint32_t (&p)[kHN / 2], const StepConsts& k,
                     uint64_t (&ls)[2]) {
       constexpr int kB = decltype(range)::kB, kE = decltype(range)::kE;
-      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, kB, kE>(sx, p, k, m_used, kHN, ls);
-      else tile_row_exp<kInt8, false, kPolyEvery, kB, kE>(sx, p, c, m_used, kHN, lsum);
+      if (QMHA_KO & 16) {   // timing experiment: no softmax arithmetic at all (tensor side alone)
+#pragma unroll
+        for (int q = kB; q < kE; ++q) p[q] = sx[2 * q];
+        return;
+      }
+      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, kB, kE>(sx, p, k, m_used, kHN, ls, one);
+      else tile_row_exp<kInt8, false, kPolyEvery, kB, kE>(sx, p, c, m_used, kHN, lsum, one);
     };
 
     // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld).  `probed` is the
     // result of an earlier non-blocking probe of the same barrier phase (keeps the barrier-unit round
     // trip off the critical path when the scores are already there, which is the normal case).
+    // kSoftRing: the scores of half-step r have arrived (s_full observed) -> hand ring stages back.
+    const bool releaser = kSoftRing && (threadIdx.x & 127) == 0;
+    auto on_scores = [&](int r) {
+      if (!kSoftRing || !releaser) return;
+      if (r & 1) mbar_arrive(&bars->k_empty[(r >> 1) % C::kStagesK]);              // K tile r/2: both halves read
+      else if (r >= 4) mbar_arrive(&bars->v_empty[((r - 4) >> 1) % C::kStagesV]);   // P.V(r-3) retired: V tile (r-4)/2
+    };
+    // "P.V(j) has retired": s_full(j+3) when that Q.K^T exists, the step's own pv_done commit otherwise
+    const int pv_c0 = n_half > 3 ? n_half - 3 : 0;   // first half-step with a pv_done commit (kLazyPv)
+    auto wait_pv = [&](int j, int site) {
+      if (kLazyPv && j + 3 < n_half)
+        mbar_wait(&bars->s_full[t][(j + 3) & 1], (uint32_t)((j + 3) >> 1) & 1, err_flag, site, dead);
+      else
+        mbar_wait(&bars->pv_done[t][j & 1], (uint32_t)((kLazyPv ? j - pv_c0 : j) >> 1) & 1, err_flag, site, dead);
+      tc_fence_after();
+    };
     auto probe = [&](int i) {
       return mbar_test_wait(&bars->s_full[t][i & 1], (uint32_t)(i >> 1) & 1) != 0;
     };
@@ -702,6 +801,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int buf = i & 1;
       if (!probed) mbar_wait(&bars->s_full[t][buf], (uint32_t)(i >> 1) & 1, err_flag, 301 + t, dead);
       tc_fence_after();
+      on_scores(i);
       tmem_ld32(tS + buf * kHN, &dst[0]);
       tmem_ld32(tS + buf * kHN + 32, &dst[32]);
     };
@@ -728,8 +828,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         l_acc *= alpha;
         // P·V(i-1) retired?  (one barrier per step parity: P·V(i-3) is known to be complete, so
         // the phase cannot alias)
-        mbar_wait(&bars->pv_done[t][(i - 1) & 1], (uint32_t)((i - 1) >> 1) & 1, err_flag, 311 + t, dead);
-        tc_fence_after();
+        wait_pv(i - 1, 311 + t);
 #pragma unroll
         for (int ch = 0; ch < kD / 32; ++ch) {
           uint32_t o[32];
@@ -788,6 +887,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int buf = (i + 1) & 1;
         if (!s_ready) mbar_wait(&bars->s_full[t][buf], (uint32_t)((i + 1) >> 1) & 1, err_flag, 301 + t, dead);
         tc_fence_after();
+        on_scores(i + 1);
         tmem_ld32(tS + buf * kHN, &nxt[0]);
         if (tracer) tr[i * 4 + 2] = clock64();
         kn = load_consts(i + 1);
@@ -795,7 +895,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld32(tS + buf * kHN + 32, &nxt[32]);
         exps(Range<kA2, kFb>{}, cur, p, kc, ls);
         tmem_wait_ld();
-        mt_nxt = row_max(nxt, kn, false, kHN);
+        mt_nxt = (QMHA_KO & 4) ? __uint_as_float(nxt[0] ^ nxt[63]) * 1e-30f : row_max(nxt, kn, false, kHN);
         raise_nxt = vote_raise(mt_nxt);
         exps(Range<kFb, kHN / 2>{}, cur, p, kc, ls);
       } else {
@@ -816,20 +916,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (vote_raise(mt)) raise_max(i, mt);
       if constexpr (kBlk) {
         uint64_t ls[2] = {0ull, 0ull};
-        if (masked) tile_row_exp_blk<true, kPolyEvery>(cur, p, kl, m_used, n_valid, ls);
-        else tile_row_exp_blk<false, kPolyEvery>(cur, p, kl, m_used, kHN, ls);
+        if (masked) tile_row_exp_blk<true, kPolyEvery>(cur, p, kl, m_used, n_valid, ls, one);
+        else tile_row_exp_blk<false, kPolyEvery>(cur, p, kl, m_used, kHN, ls, one);
         fold_sums(ls, kl);
       } else {
-        if (masked) tile_row_exp<kInt8, true, kPolyEvery>(cur, p, c, m_used, n_valid, lsum);
-        else tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum);
+        if (masked) tile_row_exp<kInt8, true, kPolyEvery>(cur, p, c, m_used, n_valid, lsum, one);
+        else tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum, one);
       }
       if (tracer) tr[i * 4 + 2] = clock64();
       // P(i) goes over P(i-2).  In the steady state the fetch of S(i+1) proves that P·V(i-2) has
       // retired; there is no S(i+1) here, so ask the tensor pipe directly.
-      if (i >= 2) {
-        mbar_wait(&bars->pv_done[t][i & 1], (uint32_t)((i - 2) >> 1) & 1, err_flag, 331 + t, dead);
-        tc_fence_after();
-      }
+      if (i >= 2) wait_pv(i - 2, 331 + t);
       publish(i, p);
     };
 
@@ -1011,6 +1108,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (prm.cycles != nullptr && threadIdx.x == 0) {   // development aid: SM clocks this CTA was resident
+    atomicAdd(prm.cycles, (unsigned long long)(clock64() - t_entry));
+    atomicAdd(prm.cycles + 1, 1ull);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1119,6 +1220,8 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)a.d);
   p.debug_no_mma = getenv("QMHA_DEBUG_NO_MMA") != nullptr;
   p.tma_store = tma_store ? 1 : 0;
+  p.one = 1;
+  p.cycles = a.cycles;
   dim3 grid((a.N + 2 * kBM - 1) / (2 * kBM), (unsigned)units, 1);
   kern<<<grid, kThreads, smem_bytes, a.stream>>>(tq, tk, tv, to, p);
   cudaError_t e = cudaGetLastError();
@@ -1134,16 +1237,23 @@ bool launch_attention(const AttnLaunch& a, std::string* err) {
   const int poly = a.variant;
   const bool blk = a.blk_scales != nullptr;
   if (blk && !a.int8) { *err = "block scales require the INT8 variant"; return false; }
+#ifndef QMHA_ONLY_D128
   if (a.trace) {
     if (!(a.int8 && a.d_pad == 128)) { *err = "tracing is only built for the INT8 d=128 kernel"; return false; }
     return blk ? launch_cfg<true, 128, 0, true, true>(a, err) : launch_cfg<true, 128, 0, false, true>(a, err);
   }
+#endif
+#ifdef QMHA_ONLY_D128   // quick experiment builds (tools/build_variant.sh): d = 128, all-MUFU exponentials only
+#define QMHA_DISPATCH(INT8, BLK, D)                                   \
+  if (D == 128 && poly == 0) return launch_cfg<INT8, 128, 0, BLK, false>(a, err);
+#else
 #define QMHA_DISPATCH(INT8, BLK, D)                                   \
   switch (poly) {                                                     \
     case 0: return launch_cfg<INT8, D, 0, BLK, false>(a, err);        \
     case 4: return launch_cfg<INT8, D, 4, BLK, false>(a, err);        \
     case 8: return launch_cfg<INT8, D, 8, BLK, false>(a, err);        \
   }
+#endif
   if (a.int8 && blk) {
     switch (a.d_pad) {
       case 32: QMHA_DISPATCH(true, true, 32) break;

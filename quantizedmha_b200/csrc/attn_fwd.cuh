@@ -22,6 +22,8 @@ struct AttnParams {
   float scale_log2;     // log2(e) / sqrt(d)
   int debug_no_mma;     // measurement aid: skip every tcgen05.mma (results are garbage)
   int tma_store;        // epilogue writes the output with TMA tensor stores (needs d % 32 == 0)
+  int one;              // 1 (a value the compiler cannot fold; see i2f_magic)
+  unsigned long long* cycles;  // development aid: {sum of CTA residency clocks, CTA count} or nullptr
 };
 
 struct AttnLaunch {
@@ -35,6 +37,7 @@ struct AttnLaunch {
   const float* blk_aux = nullptr;
   const float* blk_vmax = nullptr;
   long long* trace = nullptr;  // device buffer; non-null selects the traced instantiation
+  unsigned long long* cycles = nullptr;  // development aid (qmha_debug_cycles)
   int variant = 0;             // k > 0: exp2 of every k-th score pair on the FMA-pipe polynomial
   int B, N, H, d, n_pad, d_pad;
   bool int8;

@@ -57,9 +57,9 @@ def _err(got, ref):
     return float(np.abs(got - ref).max()), float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
 
 
-def _run(qm, torch, q, k, v, h, kernel):
+def _run(qm, torch, q, k, v, h, kernel, gran=None):
     tq, tk, tv = _dev(torch, q, k, v)
-    out = qm.forward(tq, tk, tv, h, kernel=kernel)
+    out = qm.forward(tq, tk, tv, h, kernel=kernel, gran=qm.GRAN_HEAD if gran is None else gran)
     torch.cuda.synchronize()
     qm.binding.check_async_error()
     return out.cpu().numpy()
@@ -148,30 +148,37 @@ def test_golden_cases_both_kernels(qm, torch, oracle, golden_dir, case):
     assert mx <= INT8_MAX_ABS, (case, mx, rel)   # rel-L2 on golden inputs is reported, see DESIGN.md
 
 
+@pytest.mark.parametrize("gran_name", ["head", "block"])
 @pytest.mark.parametrize("shape", [(1, 2048, 512, 4), (2, 640, 256, 2), (1, 4096, 512, 8), (1, 1000, 128, 4), (1, 2304, 128, 1)])
-def test_profile_inputs_int8_tolerance_and_two_level(qm, torch, oracle, shape):
-    """North-star contract on the reference's own profiling inputs (inputs/data.cu)."""
+def test_profile_inputs_int8_tolerance_and_two_level(qm, torch, oracle, shape, gran_name):
+    """North-star contract on the reference's own profiling inputs (inputs/data.cu), per-head scales and the
+    block scales solve() and bench.py use by default."""
     B, N, dm, h = shape
+    gran = qm.GRAN_HEAD if gran_name == "head" else qm.GRAN_BLOCK
     q, k, v = (a.reshape(B, N, dm) for a in oracle.profile_inputs(B * N, dm))
     ref = oracle.mha(q, k, v, h, "f64")
-    got = _run(qm, torch, q, k, v, h, "int8")
+    got = _run(qm, torch, q, k, v, h, "int8", gran)
     mx, rel = _err(got, ref)
     assert mx <= INT8_MAX_ABS and rel <= INT8_REL_L2, (mx, rel)
-    qq, sq = oracle.quantize(q, h, "head")
-    kq, sk = oracle.quantize(k, h, "head")
-    vq, sv = oracle.quantize(v, h, "head")
-    emu = oracle.mha_int8_emulated(qq, kq, vq, sq, sk, sv, h, "f16")
+    qq, sq = oracle.quantize(q, h, gran_name, 32)
+    kq, sk = oracle.quantize(k, h, gran_name, 32)
+    vq, sv = oracle.quantize(v, h, gran_name, 32)
+    if gran_name == "head":
+        emu = oracle.mha_int8_emulated(qq, kq, vq, sq, sk, sv, h, "f16")
+    else:
+        emu = oracle.mha_int8_emulated_block(qq, kq, vq, sq, sk, sv, h, 32, "f16")
     _, rel_k = _err(got, emu)
     assert rel_k <= KERNEL_VS_EMU_REL_L2, rel_k
     mx_f, _ = _err(_run(qm, torch, q, k, v, h, "f16"), ref)
     assert mx_f <= F16_MAX_ABS, mx_f
 
 
-def test_c3_shape_int8(qm, torch, oracle):
+@pytest.mark.parametrize("gran_name", ["GRAN_HEAD", "GRAN_BLOCK", "GRAN_TENSOR"])
+def test_c3_shape_int8(qm, torch, oracle, gran_name):
     """BASELINE config 3: B=1, H=8, N=4096, d=64."""
     q, k, v = oracle.profile_inputs(4096, 512)
     ref = oracle.mha(q, k, v, 8, "f32")
-    mx, rel = _err(_run(qm, torch, q, k, v, 8, "int8"), ref)
+    mx, rel = _err(_run(qm, torch, q, k, v, 8, "int8", getattr(qm, gran_name)), ref)
     assert mx <= INT8_MAX_ABS and rel <= INT8_REL_L2, (mx, rel)
 
 
@@ -269,12 +276,14 @@ def test_linearity_in_v_and_permutation_invariance_at_scale(qm, torch):
     assert (o8 - o1).abs().max().item() <= INT8_MAX_ABS and rel <= INT8_REL_L2
 
 
-def test_headline_shape_sampled_rows_vs_oracle(qm, torch, oracle):
-    """C4 geometry (N=8192, d=128), one batch x 2 heads end to end on the GPU; a sample of query
-    rows of each head is checked against the FP64 oracle (full rows, all 8192 keys)."""
+@pytest.mark.parametrize("gran_name", ["GRAN_HEAD", "GRAN_BLOCK"])
+def test_headline_shape_sampled_rows_vs_oracle(qm, torch, oracle, gran_name):
+    """C4 geometry (N=8192, d=128), one batch x 2 heads end to end on the GPU on the reference's own generator
+    (inputs/data.cu); a sample of query rows of each head is checked against the FP64 oracle (full rows, all
+    8192 keys).  The full B=8 x H=32 configuration is in tests/test_gpu_configs.py."""
     N, H, d = 8192, 2, 128
     q, k, v = oracle.profile_inputs(N, H * d)
-    got = _run(qm, torch, q, k, v, H, "int8")
+    got = _run(qm, torch, q, k, v, H, "int8", getattr(qm, gran_name))
     got16 = _run(qm, torch, q, k, v, H, "f16")
     rows = np.arange(0, N, 257)
     for hh in range(H):

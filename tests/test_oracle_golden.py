@@ -173,3 +173,16 @@ def test_cache_file_format_round_trip_with_reference(oracle, reflib, tmp_path):
     z = np.empty_like(x)
     assert reflib.lib.ref_load_reference(z, p2, 16, 32) == 1 and np.array_equal(x, z)
     assert oracle.lib.oracle_load_reference(p2, z, 8, 32) == 0  # header mismatch is rejected
+
+
+def test_row_sample_entry_equals_the_full_oracle(oracle):
+    """oracle.mha_head_rows (used for the C4 / C5 GPU checks, where the full output is out of reach of the
+    CPU) is the same per-row routine as oracle.mha: bit-identical in fp32, and in float64."""
+    q, k, v = oracle.golden_inputs(300, 96, 3)
+    rows = np.array([0, 7, 150, 299])
+    for prec in ("f32", "f64"):
+        full = oracle.mha(q, k, v, 3, prec)
+        for head in range(3):
+            sl = slice(head * 32, (head + 1) * 32)
+            got = oracle.mha_head_rows(q[rows][:, sl], k[:, sl], v[:, sl], prec)
+            assert np.array_equal(got, full[rows][:, sl]), (prec, head)
