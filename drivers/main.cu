@@ -90,10 +90,22 @@ int main(int argc, char** argv) {
     CHECK_CUDA(cudaDeviceSynchronize());
     std::vector<float> got(per_batch);
     CHECK_CUDA(cudaMemcpy(got.data(), dev.out, dev.bytes, cudaMemcpyDeviceToHost));
+    if (std::getenv("QMHA_DRIVER_CORRUPT")) got[got.size() / 2] += 1.0f;   // test hook: force a failed check
+    // Reference of the constant-input check, cached like the reference's driver does (drivers/main.cu:85-94,
+    // ".cache/ref_N%d_d%d.bin"): a file written by the reference's own binary is used as is; otherwise the exact
+    // answer (softmax of equal scores times a constant V = 1) is written in the same format.
+    std::vector<float> ref;
+    const std::string ref_path = ref_cache_path(pN, pD);
+    if (read_ref_cache(ref, ref_path, pN, pD)) {
+      std::printf("Loaded CPU reference from %s\n", ref_path.c_str());
+    } else {
+      ref.assign(per_batch, 1.0f);
+      if (write_ref_cache(ref, ref_path, pN, pD)) std::printf("Saved CPU reference to %s\n", ref_path.c_str());
+    }
     bool ok = *qmha_last_error() == 0;
-    for (size_t i = 0; ok && i < got.size(); ++i)
-      if (!std::isfinite(got[i]) || std::fabs(got[i] - 1.0f) > 1e-3f) {
-        std::fprintf(stderr, "Mismatch at index: %zu: got=%g ref=1 tol=0.001\n", i, got[i]);
+    for (size_t i = 0; ok && i < got.size(); ++i)   // verify_results(h_output, ref_output, 1e-3f, 1e-3f), utils/verify.cu:153-173
+      if (!std::isfinite(got[i]) || std::fabs(got[i] - ref[i]) > std::fmax(1e-3f, 1e-3f * std::fabs(ref[i]))) {
+        std::fprintf(stderr, "Mismatch at index: %zu: got=%g ref=%g tol=0.001\n", i, got[i], ref[i]);
         ok = false;
       }
     if (ok) {
@@ -144,7 +156,7 @@ int main(int argc, char** argv) {
     if (pB == 1) {
       solve(dev.q, dev.k, dev.v, dev.out, pN, pD, pH);
     } else {
-      if (qmha_forward(dev.q, dev.k, dev.v, dev.out, pB, pN, pD, pH, kid, QMHA_GRAN_HEAD, nullptr) != 0) {
+      if (qmha_forward(dev.q, dev.k, dev.v, dev.out, pB, pN, pD, pH, kid, -1, nullptr) != 0) {
         std::fprintf(stderr, "%s\n", qmha_last_error());
         std::exit(1);
       }

@@ -21,11 +21,14 @@ T* device_ptr(std::uintptr_t address) {
 // being dropped (the reference ignores CUDA errors inside launch(), include/launchers.h:27-71).
 void run(std::uintptr_t q, std::uintptr_t k, std::uintptr_t v, std::uintptr_t out, int rows,
          int width, int heads, const std::string& variant) {
-  if (qmha_set_kernel(variant.c_str()) != 0) throw std::invalid_argument(qmha_last_error());
-  solve(device_ptr<const float>(q), device_ptr<const float>(k), device_ptr<const float>(v),
-        device_ptr<float>(out), rows, width, heads);
-  const char* problem = qmha_last_error();
-  if (problem && problem[0] != '\0') throw std::runtime_error(problem);
+  // The kernel is chosen per call (no process-wide state is touched, so concurrent callers with different
+  // kernels cannot race); gran -1 = the granularity solve() uses for this shape.
+  const int kernel = qmha_kernel_from_name(variant.c_str());
+  if (kernel < 0) throw std::invalid_argument("unknown kernel '" + variant + "'");
+  if (qmha_forward(device_ptr<const float>(q), device_ptr<const float>(k), device_ptr<const float>(v),
+                   device_ptr<float>(out), 1, rows, width, heads, kernel, -1, nullptr) != 0)
+    throw std::runtime_error(qmha_last_error());
+  if (qmha_synchronize(nullptr) != 0) throw std::runtime_error(qmha_last_error());   // complete on return, like solve()
 }
 
 }  // namespace

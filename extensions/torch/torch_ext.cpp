@@ -22,8 +22,12 @@ struct Problem {
 Problem describe(const std::array<const at::Tensor*, 3>& qkv, int64_t d_model, int64_t num_heads) {
   static const char* const names[3] = {"Q", "K", "V"};
   for (const at::Tensor* t : qkv) TORCH_CHECK(t->is_cuda(), "Inputs must be CUDA tensors");
-  for (int i = 0; i < 3; ++i)
-    TORCH_CHECK(qkv[i]->scalar_type() == at::kFloat, names[i], " must be float32");
+  // float32 like the reference (torch_ext.cpp:15-17); float16 / bfloat16 are accepted as an extension
+  for (int i = 0; i < 3; ++i) {
+    const auto st = qkv[i]->scalar_type();
+    TORCH_CHECK(st == at::kFloat || st == at::kHalf || st == at::kBFloat16, names[i], " must be float32");
+    TORCH_CHECK(st == qkv[0]->scalar_type(), "Q, K, V must have the same dtype");
+  }
   for (int i = 1; i < 3; ++i)
     TORCH_CHECK(qkv[i]->sizes() == qkv[0]->sizes(), "Q, K, V must have the same shape");
   const at::Tensor& q = *qkv[0];
@@ -39,11 +43,16 @@ at::Tensor flash_solve(const at::Tensor& Q, const at::Tensor& K, const at::Tenso
   TORCH_CHECK(variant >= 0, "unknown kernel '", kernel, "'");
   const at::Tensor q = Q.contiguous(), k = K.contiguous(), v = V.contiguous();
   at::Tensor result = at::empty_like(q);
-  const int status = qmha_forward(q.data_ptr<float>(), k.data_ptr<float>(), v.data_ptr<float>(),
-                                  result.data_ptr<float>(), p.batch, p.rows, p.width, p.heads, variant,
-                                  qmha_default_granularity(p.width, p.heads),
-                                  at::cuda::getCurrentCUDAStream().stream());
-  TORCH_CHECK(status == 0, qmha_last_error());
+  const int dtype = q.scalar_type() == at::kFloat ? QMHA_DTYPE_F32 : (q.scalar_type() == at::kHalf ? QMHA_DTYPE_F16 : QMHA_DTYPE_BF16);
+  qmha_args a;
+  qmha_args_init(&a);   // kernel, granularity (-1 = what solve() uses for the shape) and stream are per-call
+  a.Q = q.data_ptr(); a.K = k.data_ptr(); a.V = v.data_ptr(); a.O = result.data_ptr();
+  a.B = p.batch; a.N = p.rows; a.d_model = p.width; a.h = p.heads;
+  a.kernel = variant;
+  a.in_dtype = a.out_dtype = dtype;
+  a.stream = at::cuda::getCurrentCUDAStream().stream();
+  // a pipeline failure recorded by an EARLIER launch on this device makes this call fail (checked without a sync)
+  TORCH_CHECK(qmha_forward_ex(&a) == 0, qmha_last_error());
   return result;
 }
 

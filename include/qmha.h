@@ -32,6 +32,12 @@ extern "C" {
 /* Kernel variants (selected per call; solve() uses the build/runtime default, see below). */
 #define QMHA_KERNEL_INT8 0 /* Q·K^T tcgen05 kind::i8, P·V kind::f16; replaces fa_tc_int8_a/b   */
 #define QMHA_KERNEL_F16 1  /* Q·K^T and P·V tcgen05 kind::f16; replaces fa_tc_v1a..v2b, fa, unfused */
+#define QMHA_KERNEL_BF16 2 /* same pipeline with bf16 operands (Q, K, P, V rounded to bf16), fp32 accumulation */
+
+/* Element types of Q, K, V and of the output in the extended entries (the reference's API is fp32 only). */
+#define QMHA_DTYPE_F32 0
+#define QMHA_DTYPE_F16 1
+#define QMHA_DTYPE_BF16 2
 
 /* Granularity of the dynamic INT8 scales (symmetric, zero-point free, fa_tc_int8_b.cu:104). */
 #define QMHA_GRAN_TENSOR 0 /* one scale per tensor                                   */
@@ -61,9 +67,32 @@ void solve(const float* Q, const float* K, const float* V, float* output, int N,
 int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B, int N,
                  int d_model, int h, int kernel, int gran, void* stream);
 
+/* Everything a call can choose, per call (nothing here reads or writes process-wide state; the fields
+ * marked "-1 = default" fall back to qmha_set_kernel / qmha_set_rope / the environment).  Initialise with
+ * qmha_args_init(), which also sets struct_size (checked by the library: header / library mismatch fails).
+ * SURVEY.md §8(b) "Data" row: batch, in/out dtype, mode, granularity, stream in one extended entry. */
+typedef struct qmha_args {
+  size_t struct_size;       /* sizeof(qmha_args)                                                        */
+  const void* Q;            /* DEVICE pointers, contiguous [B, N, d_model] of in_dtype, 16-byte aligned  */
+  const void* K;
+  const void* V;
+  void* O;                  /* [B, N, d_model] of out_dtype                                             */
+  int B, N, d_model, h;
+  int kernel;               /* QMHA_KERNEL_*; -1 = library default (what solve() uses)                   */
+  int gran;                 /* QMHA_GRAN_*;   -1 = default for the shape (qmha_granularity_for)          */
+  int in_dtype, out_dtype;  /* QMHA_DTYPE_*: 16-bit callers skip the fp32 round trip (the quantise pass
+                               then reads 2 instead of 4 bytes per element)                             */
+  int rope;                 /* fused RoPE on Q and K: 1 = on, 0 = off, -1 = process default              */
+  float rope_base;          /* used when rope == 1; <= 1 means 10000                                     */
+  int variant;              /* -1 (tuning aid: exp2 share on the FMA pipe, only in QMHA_BUILD_POLY builds)*/
+  void* stream;             /* cudaStream_t; NULL = legacy default stream                                */
+} qmha_args;
+void qmha_args_init(qmha_args* a);
+int qmha_forward_ex(const qmha_args* a);   /* asynchronous, stream-ordered like qmha_forward             */
+
 /* Same computation from HOST buffers (pageable or pinned): H2D, compute and D2H are pipelined
- * over batch×head-group chunks on internal streams; synchronous on return.  This is what
- * bench.py's `e2e` figure times. */
+ * over (batch entry, head group) chunks on internal streams — also for B = 1, the reference's own call
+ * shape — synchronous on return.  gran -1 = default for the shape.  This is what bench.py's `e2e` times. */
 int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, int B, int N,
                       int d_model, int h, int kernel, int gran);
 
@@ -83,11 +112,21 @@ int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int
                       int h, int gran, int8_t* Qp, int8_t* Kp, uint16_t* Vt, float* scales,
                       void* stream);
 
+/* Same with fp32 / fp16 / bf16 inputs and a per-call RoPE choice (rope: 1 / 0 / -1 = process default). */
+int qmha_quantize_qkv_ex(const void* Q, const void* K, const void* V, int in_dtype, int B, int N, int d_model,
+                         int h, int gran, int rope, float rope_base, int8_t* Qp, int8_t* Kp, uint16_t* Vt,
+                         float* scales, void* stream);
+
 /* fp32 -> fp16 operand conversion for the F16 variant (fa_tc_v1a.cu:267,321,348 convert on
  * load; here it is one HBM-bound pre-pass).  Qp/Kp are fp16 stored as uint16_t. */
 int qmha_convert_qkv_f16(const float* Q, const float* K, const float* V, int B, int N,
                          int d_model, int h, uint16_t* Qp, uint16_t* Kp, uint16_t* Vt,
                          void* stream);
+/* Operand conversion for the 16-bit kernels: kernel = QMHA_KERNEL_F16 (fp16 operands) or QMHA_KERNEL_BF16
+ * (bf16 operands), inputs of in_dtype. */
+int qmha_convert_qkv_16(const void* Q, const void* K, const void* V, int in_dtype, int B, int N, int d_model,
+                        int h, int kernel, int rope, float rope_base, uint16_t* Qp, uint16_t* Kp, uint16_t* Vt,
+                        void* stream);
 
 /* Reference-granularity quantisation of ONE tensor in the INPUT layout [B, N, d_model]:
  * one scale per (batch, head, block of block_rows rows) exactly like fp32_to_int8sram on a
@@ -105,9 +144,20 @@ int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt,
                             const float* scales, float* O, int B, int N, int d_model, int h,
                             int kernel, int gran, void* stream);
 
-/* qmha_forward()/qmha_attention_prepared() are asynchronous; after synchronising the stream,
- * this reports (and clears) a device-side pipeline failure recorded by the kernel. */
+int qmha_attention_prepared_ex(const void* Qp, const void* Kp, const uint16_t* Vt,
+                               const float* scales, void* O, int out_dtype, int B, int N, int d_model,
+                               int h, int kernel, int gran, void* stream);
+
+/* qmha_forward*()/qmha_attention_prepared*() are asynchronous; after synchronising the stream,
+ * this reports (and clears) a device-side pipeline failure recorded by the kernel (a bounded mbarrier
+ * wait that gave up).  Independently of this call, a failing launch also writes its record to a mapped
+ * host word that EVERY entry point checks first: the call after a stalled launch fails with that record
+ * (once) instead of silently going on, and later launches are not affected by it. */
 int qmha_check_async_error(void);
+/* cudaStreamSynchronize(stream) + qmha_check_async_error() in one call (for bindings without CUDA headers). */
+int qmha_synchronize(void* stream);
+/* Test hook: plants a failure record exactly as a stalled CTA would. */
+int qmha_debug_inject_stall(int site);
 
 /* Debug/tuning aid: runs the instrumented INT8 d=128 attention kernel once (synchronous) and
  * returns the clock64 timeline of CTA (0,0): host_trace[9][ceil(N/64)][4] (softmax warps
@@ -127,17 +177,21 @@ int qmha_debug_cycles(unsigned long long* out2, int reset);
  * inside the HBM-bound quantise / convert pass, before the block maxima are taken: position =
  * row index within the batch entry, pairs (k, k + d/2), theta = powf(base, -2k/d) exactly as
  * verify.cu:9-23 / generate_golden.cpp:38-51.  The rotated values are bit-identical to the CPU
- * restatement (cos/sin come from a host-built table).  Needs d % 8 == 0 and, for INT8,
- * QMHA_GRAN_BLOCK or QMHA_GRAN_HEAD (per-tensor scales are not covered).  Process-wide setting; QMHA_ROPE=1 in the environment enables it at start. */
+ * restatement (cos/sin come from a host-built table).  Needs d % 8 == 0; every scale granularity and the
+ * 16-bit kernels are covered.  qmha_set_rope is the process-wide DEFAULT (QMHA_ROPE=1 in the environment enables it at
+ * start); qmha_args.rope / the *_ex entries choose per call. */
 int qmha_set_rope(int enable, float base);
 int qmha_get_rope(void);
 
 /* ---- housekeeping -------------------------------------------------------------------------- */
 const char* qmha_last_error(void);          /* "" when the last call on this thread succeeded */
 int qmha_set_kernel(const char* name);      /* default variant used by solve(); 0 = ok        */
-const char* qmha_get_kernel(void);          /* "int8" or "f16"                                */
-int qmha_default_granularity(int d_model, int h); /* what solve() uses: QMHA_GRAN_BLOCK when d%4==0
-                                                     (QMHA_SCALES=head|tensor overrides), else HEAD  */
+const char* qmha_get_kernel(void);          /* "int8", "f16" or "bf16"                        */
+int qmha_default_granularity(int d_model, int h); /* QMHA_GRAN_BLOCK when d%4==0 (QMHA_SCALES=head|tensor
+                                                     overrides), else HEAD                            */
+int qmha_granularity_for(int N, int d_model, int h); /* what solve() uses: the same, but HEAD when the per-block
+                                                     scale table of one unit no longer fits in shared
+                                                     memory behind the tiles (N > ~68 k at d = 128)  */
 int qmha_kernel_from_name(const char* name); /* QMHA_KERNEL_* or -1                           */
 int64_t qmha_launch_count(void);            /* kernels launched by this library so far        */
 void qmha_shutdown(void);                   /* frees every per-device workspace               */

@@ -178,6 +178,11 @@ class RefLib:
         L.ref_save_reference.restype = C.c_int
         L.ref_load_reference.argtypes = [_f32p, C.c_char_p, C.c_int, C.c_int]
         L.ref_load_reference.restype = C.c_int
+        if hasattr(L, "ref_load_inputs"):
+            L.ref_save_inputs.argtypes = [_f32p, _f32p, _f32p, C.c_char_p, C.c_int, C.c_int]
+            L.ref_save_inputs.restype = C.c_int
+            L.ref_load_inputs.argtypes = [_f32p, _f32p, _f32p, C.c_char_p, C.c_int, C.c_int]
+            L.ref_load_inputs.restype = C.c_int
 
     def cpu_mha(self, q, k, v, h):
         q, k, v = (np.ascontiguousarray(a, np.float32) for a in (q, k, v))
@@ -206,6 +211,25 @@ class RefLib:
         out = np.ascontiguousarray(out, np.float32).ravel()
         ref = np.ascontiguousarray(ref, np.float32).ravel()
         return bool(self.lib.ref_verify_results(out, ref, out.size, eps, rel))
+
+    def load_inputs(self, path, N, d_model):
+        """inputs/data.cu:84-109 load_inputs; None when the file is missing or its header does not match."""
+        q, k, v = (np.empty((N, d_model), np.float32) for _ in range(3))
+        ok = self.lib.ref_load_inputs(q, k, v, str(path).encode(), N, d_model)
+        return (q, k, v) if ok else None
+
+    def save_inputs(self, q, k, v, path):
+        q, k, v = (np.ascontiguousarray(a, np.float32) for a in (q, k, v))
+        return bool(self.lib.ref_save_inputs(q, k, v, str(path).encode(), q.shape[0], q.shape[1]))
+
+    def load_reference(self, path, N, d_model):
+        """utils/verify.cu:128-151 load_reference."""
+        o = np.empty((N, d_model), np.float32)
+        return o if self.lib.ref_load_reference(o, str(path).encode(), N, d_model) else None
+
+    def save_reference(self, data, path):
+        data = np.ascontiguousarray(data, np.float32)
+        return bool(self.lib.ref_save_reference(data, str(path).encode(), data.shape[0], data.shape[1]))
 
     def apply_rope_row(self, row, pos):
         row = np.ascontiguousarray(row, np.float32).copy()

@@ -48,4 +48,29 @@ int ref_load_reference(float* data, const char* path, int N, int d_model) {
   return 1;
 }
 
+// inputs/data.cu:54-109 (".cache/input_random_N%d_d%d.bin")
+int ref_save_inputs(const float* Q, const float* K, const float* V, const char* path, int N, int d_model) {
+  const size_t n = (size_t)N * d_model;
+  std::vector<float> q(Q, Q + n), k(K, K + n), v(V, V + n);
+  FILE* saved = stdout;
+  FILE* devnull = fopen("/dev/null", "w");
+  if (devnull) stdout = devnull;
+  const bool ok = save_inputs(q, k, v, path, N, d_model);
+  if (devnull) { stdout = saved; fclose(devnull); }
+  return ok ? 1 : 0;
+}
+int ref_load_inputs(float* Q, float* K, float* V, const char* path, int N, int d_model) {
+  std::vector<float> q, k, v;
+  FILE* saved = stdout;
+  FILE* devnull = fopen("/dev/null", "w");
+  if (devnull) stdout = devnull;
+  const bool ok = load_inputs(q, k, v, path, N, d_model);
+  if (devnull) { stdout = saved; fclose(devnull); }
+  if (!ok) return 0;
+  std::copy(q.begin(), q.end(), Q);
+  std::copy(k.begin(), k.end(), K);
+  std::copy(v.begin(), v.end(), V);
+  return 1;
+}
+
 }  // extern "C"

@@ -6,10 +6,15 @@ include/qmha.h.  There is no CPU or PyTorch fallback: if libqmha.so is missing, 
 present, every compute call raises.
 """
 from .binding import (  # noqa: F401
+    QmhaArgs,
     QmhaError,
     GRAN_BLOCK,
     GRAN_HEAD,
     GRAN_TENSOR,
+    DTYPE_BF16,
+    DTYPE_F16,
+    DTYPE_F32,
+    KERNEL_BF16,
     KERNEL_F16,
     KERNEL_INT8,
     attention_prepared,

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 from typing import Optional, Tuple
 
-KERNEL_INT8, KERNEL_F16 = 0, 1
+KERNEL_INT8, KERNEL_F16, KERNEL_BF16 = 0, 1, 2
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 GRAN_TENSOR, GRAN_HEAD, GRAN_BLOCK = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -22,6 +23,14 @@ class QmhaError(RuntimeError):
 
 def lib_path() -> str:
     return os.environ.get("QMHA_LIB", os.path.join(_HERE, "lib", "libqmha.so"))
+
+
+class QmhaArgs(C.Structure):
+    """include/qmha.h: qmha_args"""
+    _fields_ = [("struct_size", C.c_size_t), ("Q", C.c_void_p), ("K", C.c_void_p), ("V", C.c_void_p), ("O", C.c_void_p),
+                ("B", C.c_int), ("N", C.c_int), ("d_model", C.c_int), ("h", C.c_int), ("kernel", C.c_int),
+                ("gran", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("rope", C.c_int),
+                ("rope_base", C.c_float), ("variant", C.c_int), ("stream", C.c_void_p)]
 
 
 def declare(L: C.CDLL) -> C.CDLL:
@@ -38,6 +47,15 @@ def declare(L: C.CDLL) -> C.CDLL:
     L.qmha_quantize_blocks.argtypes = [vp, i, i, i, i, i, vp, vp, vp]
     L.qmha_quantize_static.argtypes = [vp, C.c_int64, f, f, vp, vp]
     L.qmha_attention_prepared.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    L.qmha_quantize_qkv_ex.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, f, vp, vp, vp, vp, vp]
+    L.qmha_convert_qkv_16.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, f, vp, vp, vp, vp]
+    L.qmha_attention_prepared_ex.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    L.qmha_forward_ex.argtypes = [C.POINTER(QmhaArgs)]
+    L.qmha_args_init.argtypes = [C.POINTER(QmhaArgs)]
+    L.qmha_args_init.restype = None
+    L.qmha_granularity_for.argtypes = [i, i, i]
+    L.qmha_debug_inject_stall.argtypes = [i]
+    L.qmha_synchronize.argtypes = [vp]
     L.qmha_check_async_error.argtypes = []
     L.qmha_last_error.restype = C.c_char_p
     L.qmha_set_kernel.argtypes = [C.c_char_p]
@@ -120,15 +138,25 @@ def _shape3(t) -> Tuple[int, int, int]:
     raise QmhaError("expected [N, d_model] or [B, N, d_model]")
 
 
-def _check_inputs(Q, K, V):
+def _dtype_id(dt) -> int:
+    torch = _torch()
+    try:
+        return {torch.float32: DTYPE_F32, torch.float16: DTYPE_F16, torch.bfloat16: DTYPE_BF16}[dt]
+    except KeyError:
+        raise QmhaError(f"unsupported dtype {dt}: float32, float16 or bfloat16") from None
+
+
+def _check_inputs(Q, K, V, allow16: bool = False):
     torch = _torch()
     for name, t in (("Q", Q), ("K", K), ("V", V)):
         if not t.is_cuda:
             raise QmhaError("Inputs must be CUDA tensors")  # torch_ext.cpp:14
-        if t.dtype != torch.float32:
+        if t.dtype != torch.float32 and not (allow16 and t.dtype in (torch.float16, torch.bfloat16)):
             raise QmhaError(f"{name} must be float32")  # torch_ext.cpp:15-17
     if Q.shape != K.shape or Q.shape != V.shape:
         raise QmhaError("Q, K, V must have the same shape")
+    if Q.dtype != K.dtype or Q.dtype != V.dtype:
+        raise QmhaError("Q, K, V must have the same dtype")
 
 
 def solve(Q, K, V, N: int, d_model: int, h: int, out=None):
@@ -143,15 +171,28 @@ def solve(Q, K, V, N: int, d_model: int, h: int, out=None):
     return out
 
 
-def forward(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=None, stream=None):
-    """Stream-ordered forward on [N, d_model] or [B, N, d_model] fp32 CUDA tensors."""
+def forward(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=None, stream=None,
+            rope=None, rope_base: float = 10000.0, out_dtype=None):
+    """Stream-ordered forward on [N, d_model] or [B, N, d_model] CUDA tensors (qmha_forward_ex).
+    Q, K, V: float32 like the reference, or float16 / bfloat16 (the quantise pass then reads 2 bytes per
+    element); out_dtype: dtype of the result (default: that of Q).  rope: True / False per call, None = the
+    process default (set_rope / QMHA_ROPE).  gran: GRAN_* or -1 = default for the shape."""
     torch = _torch()
-    _check_inputs(Q, K, V)
+    _check_inputs(Q, K, V, allow16=True)
     Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
     B, N, d_model = _shape3(Q)
-    out = torch.empty_like(Q) if out is None else out
-    _check(lib().qmha_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr(), B, N, d_model,
-                              num_heads, kernel_id(kernel), gran, _stream_ptr(stream)))
+    if out is None:
+        out = torch.empty(Q.shape, dtype=out_dtype or Q.dtype, device=Q.device)
+    a = QmhaArgs()
+    lib().qmha_args_init(C.byref(a))
+    a.Q, a.K, a.V, a.O = Q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr()
+    a.B, a.N, a.d_model, a.h = B, N, d_model, num_heads
+    a.kernel, a.gran = kernel_id(kernel), gran
+    a.in_dtype, a.out_dtype = _dtype_id(Q.dtype), _dtype_id(out.dtype)
+    a.rope = -1 if rope is None else int(bool(rope))
+    a.rope_base = float(rope_base)
+    a.stream = _stream_ptr(stream)
+    _check(lib().qmha_forward_ex(C.byref(a)))
     return out
 
 
@@ -169,9 +210,9 @@ def flash_solve(Q, K, V, d_model: int, num_heads: int, kernel: str = "fa_tc_int8
     else:
         B, N = 1, Qc.numel() // d_model
     out = torch.empty_like(Qc)
-    gran = lib().qmha_default_granularity(d_model, num_heads)   # same choice as the C solve()
+    # gran -1: the same choice as the C solve() (block scales when they fit, per-head otherwise)
     _check(lib().qmha_forward(Qc.data_ptr(), Kc.data_ptr(), Vc.data_ptr(), out.data_ptr(), B, N, d_model,
-                              num_heads, kernel_id(kernel), gran, _stream_ptr()))
+                              num_heads, kernel_id(kernel), -1, _stream_ptr()))
     return out
 
 
@@ -179,14 +220,14 @@ def flash_solve_ptr(q_ptr: int, k_ptr: int, v_ptr: int, out_ptr: int, N: int, d_
                     num_heads: int, kernel: str = "fa_tc_int8_b") -> None:
     """Mirror of jax_ext.flash_solve (extensions/jax/jax_ext.cpp:12-28): raw device addresses."""
     L = lib()
-    _check(L.qmha_forward(q_ptr, k_ptr, v_ptr, out_ptr, 1, N, d_model, num_heads, kernel_id(kernel),
-                          L.qmha_default_granularity(d_model, num_heads), None))
+    _check(L.qmha_forward(q_ptr, k_ptr, v_ptr, out_ptr, 1, N, d_model, num_heads, kernel_id(kernel), -1, None))
     _torch().cuda.synchronize()
     _check(L.qmha_check_async_error())
 
 
 def forward_host(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=None):
-    """Host (CPU, ideally pinned) fp32 tensors in, host tensor out; copies are pipelined inside."""
+    """Host (CPU, ideally pinned) fp32 tensors in, host tensor out; copies are pipelined over
+    (batch entry, head group) chunks inside."""
     torch = _torch()
     B, N, d_model = _shape3(Q)
     out = torch.empty_like(Q) if out is None else out
@@ -195,11 +236,11 @@ def forward_host(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, 
     return out
 
 
-def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None):
+def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None, rope=None, rope_base: float = 10000.0):
     """Kernel (a).  Returns (Qp int8 [B*h,n_pad,d_pad], Kp, Vt fp16 [B*h,d_pad,n_pad], scales [3,B*h]
-    or, for GRAN_BLOCK, [3,B*h,n_pad/32])."""
+    or, for GRAN_BLOCK, [3,B*h,n_pad/32]).  Inputs: float32, float16 or bfloat16."""
     torch = _torch()
-    _check_inputs(Q, K, V)
+    _check_inputs(Q, K, V, allow16=True)
     Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
     B, N, d_model = _shape3(Q)
     n_pad, d_pad = workspace_dims(N, d_model, num_heads)
@@ -211,24 +252,29 @@ def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None):
         scales = torch.empty((3, u, n_pad // 32), dtype=torch.float32, device=Q.device)
     else:
         scales = torch.empty((3, u), dtype=torch.float32, device=Q.device)
-    _check(lib().qmha_quantize_qkv(Q.data_ptr(), K.data_ptr(), V.data_ptr(), B, N, d_model, num_heads, gran,
-                                   Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), scales.data_ptr(),
-                                   _stream_ptr(stream)))
+    _check(lib().qmha_quantize_qkv_ex(Q.data_ptr(), K.data_ptr(), V.data_ptr(), _dtype_id(Q.dtype), B, N, d_model,
+                                      num_heads, gran, -1 if rope is None else int(bool(rope)), float(rope_base),
+                                      Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), scales.data_ptr(),
+                                      _stream_ptr(stream)))
     return Qp, Kp, Vt, scales
 
 
-def convert_qkv_f16(Q, K, V, num_heads: int, stream=None):
+def convert_qkv_f16(Q, K, V, num_heads: int, stream=None, kernel="f16"):
+    """Operands of the 16-bit kernels: fp16 (kernel="f16") or bf16 (kernel="bf16") tensors in the prepared layout."""
     torch = _torch()
-    _check_inputs(Q, K, V)
+    _check_inputs(Q, K, V, allow16=True)
     Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
     B, N, d_model = _shape3(Q)
     n_pad, d_pad = workspace_dims(N, d_model, num_heads)
     u = B * num_heads
-    Qp = torch.empty((u, n_pad, d_pad), dtype=torch.float16, device=Q.device)
+    kid = kernel_id(kernel)
+    dt = torch.bfloat16 if kid == KERNEL_BF16 else torch.float16
+    Qp = torch.empty((u, n_pad, d_pad), dtype=dt, device=Q.device)
     Kp = torch.empty_like(Qp)
-    Vt = torch.empty((u, d_pad, n_pad), dtype=torch.float16, device=Q.device)
-    _check(lib().qmha_convert_qkv_f16(Q.data_ptr(), K.data_ptr(), V.data_ptr(), B, N, d_model, num_heads,
-                                      Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), _stream_ptr(stream)))
+    Vt = torch.empty((u, d_pad, n_pad), dtype=dt, device=Q.device)
+    _check(lib().qmha_convert_qkv_16(Q.data_ptr(), K.data_ptr(), V.data_ptr(), _dtype_id(Q.dtype), B, N, d_model,
+                                     num_heads, kid, -1, 0.0, Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(),
+                                     _stream_ptr(stream)))
     return Qp, Kp, Vt
 
 

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -26,12 +27,15 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<unsigned> g_launch_seq{0};
 std::mutex g_mu;
-int g_default_kernel = -2;  // -2 = not resolved yet
+// Process-wide defaults (only what solve() and the *_default paths use; every extended entry can override
+// them per call through qmha_args).  Atomics: they are read by concurrent callers.
+std::atomic<int> g_default_kernel{-2};  // -2 = not resolved yet
 // Fused RoPE on Q and K inside the quantise / convert pass (qmha_set_rope; QMHA_ROPE=1 in the
 // environment turns it on for processes that only call solve(), e.g. bin/profile_* --rope).
-int g_rope = -1;            // -1 = not resolved yet (environment), 0 = off, 1 = on
-float g_rope_base = 10000.0f;
+std::atomic<int> g_rope{-1};            // -1 = not resolved yet (environment), 0 = off, 1 = on
+std::atomic<float> g_rope_base{10000.0f};
 
 int fail(const std::string& msg) {
   g_err = msg;
@@ -41,6 +45,19 @@ int fail_cuda(const char* what, cudaError_t e) {
   return fail(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+struct RopeTable {
+  float2* dev = nullptr;
+  int n = 0;
+};
+
+// Staging of qmha_forward_host: one slot = device copies of one (batch entry, head group) chunk of Q, K, V
+// and O plus the stream that carries its H2D copy, kernels and D2H copy.
+struct HostSlot {
+  float *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr;
+  cudaStream_t s = nullptr;
+};
+constexpr int kHostSlots = 3;
+
 struct Workspace {
   void* Qp = nullptr;
   void* Kp = nullptr;
@@ -49,12 +66,17 @@ struct Workspace {
   unsigned* amax = nullptr;
   float* aux = nullptr;    // block mode: [units][n_pad/32][2]
   float* vmax = nullptr;   // block mode: [units]
-  int* error_flag = nullptr;
+  int* error_flag = nullptr;        // device: (launch id << 12) | wait site of the last stalled launch
+  int* error_host = nullptr;        // mapped host word: wait site, written by the failing CTA
+  int* error_host_dev = nullptr;    // its device address
   unsigned long long* cycles = nullptr;  // {sum of CTA residency clocks, CTAs}: qmha_debug_cycles
   size_t qk_bytes = 0, vt_bytes = 0, scale_elems = 0;
-  float2* rope_tab = nullptr;  // {cos, sin}[rope_n][rope_d/2] for rope_base
-  int rope_n = 0, rope_d = 0;
-  float rope_base = 0.f;
+  // {cos, sin}[n][d/2] tables keyed by (d, base bits); grown tables replace their predecessor only in the
+  // map — the old allocation stays alive until qmha_shutdown (a launch already enqueued may still read it).
+  std::map<std::pair<int, uint32_t>, RopeTable> rope;
+  std::vector<float2*> rope_retired;
+  HostSlot host_slots[kHostSlots];
+  size_t host_slot_elems = 0;
   // The workspace is shared by every call on the device.  `call_mu` serialises the host-side enqueue
   // sequences (and any growth) of concurrent callers; `last_use` is recorded behind the last enqueued
   // work that touches the workspace, and a call on another stream waits for it on the device first
@@ -131,6 +153,14 @@ int get_workspace(int dev, size_t qk_bytes, size_t vt_bytes, size_t scale_elems,
   if (!w.error_flag) {
     if ((e = cudaMalloc(&w.error_flag, sizeof(int))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     cudaMemset(w.error_flag, 0, sizeof(int));
+    // host-visible copy of the failure record: checked (without synchronising) at the start of every call
+    if (cudaHostAlloc(&w.error_host, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+      *w.error_host = 0;
+      if (cudaHostGetDevicePointer(&w.error_host_dev, w.error_host, 0) != cudaSuccess) w.error_host_dev = nullptr;
+    } else {
+      w.error_host = nullptr;
+      cudaGetLastError();
+    }
   }
   if (!w.cycles && getenv("QMHA_CYCLES")) {
     if ((e = cudaMalloc(&w.cycles, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
@@ -156,7 +186,7 @@ int get_workspace(int dev, size_t qk_bytes, size_t vt_bytes, size_t scale_elems,
     cudaFree(w.scales); cudaFree(w.amax); cudaFree(w.aux); cudaFree(w.vmax);
     w.scales = nullptr; w.amax = nullptr; w.aux = nullptr; w.vmax = nullptr; w.scale_elems = 0;
     if ((e = cudaMalloc(&w.scales, scale_elems * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc(scales)", e);
-    if ((e = cudaMalloc(&w.amax, scale_elems * sizeof(unsigned))) != cudaSuccess) return fail_cuda("cudaMalloc(amax)", e);
+    if ((e = cudaMalloc(&w.amax, (2 * scale_elems + 64) * sizeof(unsigned))) != cudaSuccess) return fail_cuda("cudaMalloc(amax)", e);
     if ((e = cudaMalloc(&w.aux, scale_elems * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc(aux)", e);
     if ((e = cudaMalloc(&w.vmax, scale_elems * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc(vmax)", e);
     w.scale_elems = scale_elems;
@@ -171,47 +201,91 @@ int check_aligned16(const void* p, const char* name) {
   return 0;
 }
 
-// Reads and clears the device-side error flag (set when an mbarrier wait timed out).
+std::string stall_message(int site) {
+  return "attention kernel pipeline stalled at wait site " + std::to_string(site) +
+         ": the output of that launch is incomplete";
+}
+
+// A launch that stalled leaves its record in the mapped host word: every entry point looks at it first
+// (no synchronisation), fails THAT call and clears the record — a stall cannot pass unnoticed just
+// because the caller never asks qmha_check_async_error().  Later launches are not affected by the
+// record (the kernel compares launch ids), so the call after the failing one runs normally.
+int fail_on_recorded_stall(Workspace* w) {
+  if (!w->error_host) return 0;
+  const int site = *(volatile int*)w->error_host;
+  if (site == 0) return 0;
+  *(volatile int*)w->error_host = 0;
+  cudaMemsetAsync(w->error_flag, 0, sizeof(int), nullptr);
+  return fail("an earlier launch on this device failed: " + stall_message(site));
+}
+
+// Reads and clears the device-side error record after the caller synchronised.
 int check_error_flag(Workspace* w) {
   int flag = 0;
   cudaError_t e = cudaMemcpy(&flag, w->error_flag, sizeof(int), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return fail_cuda("reading kernel error flag", e);
   if (flag != 0) {
     cudaMemset(w->error_flag, 0, sizeof(int));
-    return fail("attention kernel pipeline stalled at wait site " + std::to_string(flag));
+    if (w->error_host) *(volatile int*)w->error_host = 0;
+    return fail(stall_message(flag & 0xFFF));
   }
   return 0;
 }
 
+unsigned next_launch_id() {
+  unsigned id;
+  do { id = (g_launch_seq.fetch_add(1) + 1) & 0xFFFFFu; } while (id == 0);
+  return id;
+}
+
 int resolve_default_kernel() {
-  if (g_default_kernel == -2) {
+  int k = g_default_kernel.load();
+  if (k == -2) {
     const char* env = getenv("QMHA_KERNEL");
-    int k = qmha_kernel_from_name(env && *env ? env : QMHA_DEFAULT_KERNEL);
-    g_default_kernel = k < 0 ? QMHA_KERNEL_INT8 : k;
+    k = qmha_kernel_from_name(env && *env ? env : QMHA_DEFAULT_KERNEL);
+    if (k < 0) k = QMHA_KERNEL_INT8;
+    g_default_kernel.store(k);
   }
-  return g_default_kernel;
+  return k;
 }
 
 size_t scale_count(int units, int n_pad, int gran) {
   return gran == QMHA_GRAN_BLOCK ? (size_t)3 * units * (n_pad / 32) : (size_t)3 * units;
 }
 
-bool rope_enabled() {
-  if (g_rope < 0) {
+bool rope_default() {
+  int r = g_rope.load();
+  if (r < 0) {
     const char* env = getenv("QMHA_ROPE");
-    g_rope = (env && *env && *env != '0') ? 1 : 0;
+    r = (env && *env && *env != '0') ? 1 : 0;
+    g_rope.store(r);
   }
-  return g_rope == 1;
+  return r == 1;
+}
+
+// What solve() uses: the reference's own granularity (one scale per 32-row block) whenever the
+// vectorised single-pass quantiser applies and the per-block table of one unit fits in shared memory
+// behind the tiles (N <= ~68 k at d = 128); per (batch, head) otherwise.
+int default_granularity(int N, int d_model, int h) {
+  const char* env = getenv("QMHA_SCALES");
+  if (env && !strcmp(env, "head")) return QMHA_GRAN_HEAD;
+  if (env && !strcmp(env, "tensor")) return QMHA_GRAN_TENSOR;
+  if (h > 0 && d_model % h == 0 && ((d_model / h) & 3) == 0) {
+    const int dp = pad_head_dim(d_model / h);
+    if (dp > 0 && (N <= 0 || round_up(N, 256) <= qmha::attention_max_block_keys(dp))) return QMHA_GRAN_BLOCK;
+  }
+  return QMHA_GRAN_HEAD;
 }
 
 // {cos, sin} table of the reference's RoPE (utils/verify.cu:9-23: theta = powf(base, -2k/d),
 // angle = pos * theta, sinf / cosf), computed with the host's libm — the same functions the CPU
-// reference calls — so the fused rotation reproduces its fp32 values bit for bit.  Cached per
-// device for the largest N seen with this (d, base).
-int get_rope_table(int dev, int N, int d, float base, const float2** out) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  Workspace& w = g_ws[dev];
-  if (w.rope_tab && w.rope_d == d && w.rope_base == base && w.rope_n >= N) { *out = w.rope_tab; return 0; }
+// reference calls — so the fused rotation reproduces its fp32 values bit for bit.  One table per
+// (device, d, base), grown to the largest N seen.  The caller holds the workspace's call lock.
+int get_rope_table(Workspace* w, int N, int d, float base, const float2** out) {
+  uint32_t bits;
+  memcpy(&bits, &base, sizeof(bits));
+  RopeTable& t = w->rope[std::make_pair(d, bits)];
+  if (t.dev && t.n >= N) { *out = t.dev; return 0; }
   const int half = d / 2;
   std::vector<float2> tab((size_t)N * half);
   std::vector<float> theta(half);
@@ -221,37 +295,50 @@ int get_rope_table(int dev, int N, int d, float base, const float2** out) {
       const float angle = pos * theta[k];
       tab[(size_t)pos * half + k] = make_float2(cosf(angle), sinf(angle));
     }
-  cudaDeviceSynchronize();
-  cudaFree(w.rope_tab);
-  w.rope_tab = nullptr; w.rope_n = 0;
-  cudaError_t e = cudaMalloc(&w.rope_tab, tab.size() * sizeof(float2));
+  float2* dev = nullptr;
+  cudaError_t e = cudaMalloc(&dev, tab.size() * sizeof(float2));
   if (e != cudaSuccess) return fail_cuda("cudaMalloc(rope table)", e);
-  e = cudaMemcpy(w.rope_tab, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) return fail_cuda("uploading the rope table", e);
-  w.rope_n = N; w.rope_d = d; w.rope_base = base;
-  *out = w.rope_tab;
+  e = cudaMemcpy(dev, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(dev); return fail_cuda("uploading the rope table", e); }
+  if (t.dev) w->rope_retired.push_back(t.dev);   // may still be read by an enqueued launch
+  t.dev = dev; t.n = N;
+  *out = dev;
   return 0;
 }
 
-int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, int d_model, int h,
-                 int kernel, int gran, void* Qp, void* Kp, void* Vt, float* scales, unsigned* amax,
-                 cudaStream_t stream) {
+bool dtype_ok(int dt) { return dt == QMHA_DTYPE_F32 || dt == QMHA_DTYPE_F16 || dt == QMHA_DTYPE_BF16; }
+bool kernel_ok(int k) { return k == QMHA_KERNEL_INT8 || k == QMHA_KERNEL_F16 || k == QMHA_KERNEL_BF16; }
+
+struct RopeOpt {
+  bool on = false;
+  float base = 10000.0f;
+};
+RopeOpt rope_from(int rope, float base) {   // -1 = process default
+  RopeOpt r;
+  if (rope < 0) { r.on = rope_default(); r.base = g_rope_base.load(); }
+  else { r.on = rope != 0; r.base = base > 1.0f ? base : 10000.0f; }
+  return r;
+}
+
+// The caller holds the call lock of `w` (the rope tables live in the workspace).
+int prepare_impl(Workspace* w, const void* Q, const void* K, const void* V, int in_dtype, int B, int N,
+                 int d_model, int h, int kernel, int gran, const RopeOpt& rope, void* Qp, void* Kp, void* Vt,
+                 float* scales, unsigned* amax, cudaStream_t stream) {
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
+  if (!dtype_ok(in_dtype)) return fail("unknown input dtype");
   if (check_aligned16(Q, "Q") || check_aligned16(K, "K") || check_aligned16(V, "V")) return 1;
+  if (in_dtype != QMHA_DTYPE_F32 && (d & 3) != 0)
+    return fail("16-bit inputs need a head dimension that is a multiple of 4");
   qmha::PrepareArgs a;
-  a.Q = Q; a.K = K; a.V = V; a.scales = scales; a.Qp = Qp; a.Kp = Kp; a.Vt = Vt;
+  a.Q = Q; a.K = K; a.V = V; a.in_dtype = in_dtype; a.scales = scales; a.Qp = Qp; a.Kp = Kp; a.Vt = Vt;
   a.B = B; a.N = N; a.H = h; a.d = d; a.n_pad = n_pad; a.d_pad = d_pad;
   a.int8 = kernel == QMHA_KERNEL_INT8;
+  a.bf16 = kernel == QMHA_KERNEL_BF16;
   a.stream = stream;
-  if (rope_enabled()) {
+  if (rope.on) {
     if ((d & 7) != 0) return fail("fused RoPE needs a head dimension that is a multiple of 8");
-    static const bool two_pass = getenv("QMHA_TWO_PASS_QUANT") != nullptr;
-    if (a.int8 && !(gran == QMHA_GRAN_BLOCK || (gran == QMHA_GRAN_HEAD && !two_pass)))
-      return fail("fused RoPE is implemented for QMHA_GRAN_BLOCK / QMHA_GRAN_HEAD (INT8) and for the F16 kernel");
-    int dev = -1;
-    cudaGetDevice(&dev);
-    if (get_rope_table(dev, N, d, g_rope_base, &a.rope)) return 1;
+    if (get_rope_table(w, N, d, rope.base, &a.rope)) return 1;
   }
   cudaError_t e;
   if (a.int8) {
@@ -267,7 +354,12 @@ int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, i
     // scales need a global maximum first and keep the two-pass path (as does an odd head dim).
     static const bool two_pass_env = getenv("QMHA_TWO_PASS_QUANT") != nullptr;
     if (gran == QMHA_GRAN_HEAD && (d & 3) == 0 && !two_pass_env) {
-      if ((e = qmha::launch_fused_quantize(a)) != cudaSuccess) return fail_cuda("fused quantise launch", e);
+      static const bool cluster_env = getenv("QMHA_CLUSTER_QUANT") != nullptr;   // the older cluster kernel, for A/B
+      if (cluster_env) {
+        if ((e = qmha::launch_fused_quantize(a)) != cudaSuccess) return fail_cuda("fused quantise launch", e);
+      } else {
+        if ((e = qmha::launch_stream_quantize(a, amax)) != cudaSuccess) return fail_cuda("stream quantise launch", e);
+      }
       g_launches += 1;
       return 0;
     }
@@ -280,33 +372,36 @@ int prepare_impl(const float* Q, const float* K, const float* V, int B, int N, i
   return 0;
 }
 
-// Kernel variant k: exp2 of every k-th score pair on the FMA-pipe polynomial (0 = all MUFU).
-// QMHA_ATTN_VARIANT overrides the built-in default (tuning / A-B measurements).
-int attention_variant(int kernel) {
-  const char* env = getenv("QMHA_ATTN_VARIANT");
-  if (env && *env) return atoi(env);
-  (void)kernel;
-  return QMHA_DEFAULT_ATTN_VARIANT;
+// Kernel variant k: exp2 of every k-th score pair on the FMA-pipe polynomial (0 = all MUFU; other values
+// exist only in -DQMHA_BUILD_POLY builds).  QMHA_ATTN_VARIANT overrides the built-in default.
+int attention_variant() {
+  static const int v = [] {
+    const char* env = getenv("QMHA_ATTN_VARIANT");
+    return env && *env ? atoi(env) : QMHA_DEFAULT_ATTN_VARIANT;
+  }();
+  return v;
 }
 
 // scales: [3][B*h] (per-head / per-tensor) or, for gran == QMHA_GRAN_BLOCK, [3][B*h][n_pad/32];
 // aux / vmax: scratch of the same element count used only in block mode.
-int attention_impl(const void* Qp, const void* Kp, const void* Vt, const float* scales, float* O,
-                   int B, int N, int d_model, int h, int kernel, int* error_flag,
-                   cudaStream_t stream, long long* trace = nullptr, int variant = -1,
-                   int gran = QMHA_GRAN_HEAD, float* aux = nullptr, float* vmax = nullptr,
-                   unsigned long long* cycles = nullptr) {
+int attention_impl(Workspace* w, const void* Qp, const void* Kp, const void* Vt, const float* scales, void* O,
+                   int out_dtype, int B, int N, int d_model, int h, int kernel, cudaStream_t stream,
+                   long long* trace = nullptr, int variant = -1, int gran = QMHA_GRAN_HEAD,
+                   float* aux = nullptr, float* vmax = nullptr, unsigned long long* cycles = nullptr) {
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
+  if (!dtype_ok(out_dtype)) return fail("unknown output dtype");
   if (check_aligned16(O, "output")) return 1;
   qmha::AttnLaunch a;
-  a.Qp = Qp; a.Kp = Kp; a.Vt = Vt; a.scales = scales; a.O = O; a.error_flag = error_flag;
+  a.Qp = Qp; a.Kp = Kp; a.Vt = Vt; a.scales = scales; a.O = O; a.out_dtype = out_dtype;
+  a.error_flag = w->error_flag; a.error_host = w->error_host_dev; a.launch_id = next_launch_id();
   a.B = B; a.N = N; a.H = h; a.d = d; a.n_pad = n_pad; a.d_pad = d_pad;
   a.int8 = kernel == QMHA_KERNEL_INT8;
+  a.bf16 = kernel == QMHA_KERNEL_BF16;
   a.stream = stream;
   a.trace = trace;
   a.cycles = cycles;
-  a.variant = variant >= 0 ? variant : attention_variant(kernel);
+  a.variant = variant >= 0 ? variant : attention_variant();
   if (a.int8 && gran == QMHA_GRAN_BLOCK) {
     if (!aux || !vmax) return fail("internal: block mode needs scratch");
     const int units = B * h, nblk = n_pad / 32;
@@ -323,12 +418,63 @@ int attention_impl(const void* Qp, const void* Kp, const void* Vt, const float* 
   return 0;
 }
 
+// Resolves the "-1 = default" fields of a qmha_args copy and validates it.
+int resolve_args(qmha_args* a) {
+  if (a->kernel < 0) a->kernel = resolve_default_kernel();
+  if (!kernel_ok(a->kernel)) return fail("unknown kernel id");
+  if (!dtype_ok(a->in_dtype) || !dtype_ok(a->out_dtype)) return fail("unknown dtype (QMHA_DTYPE_F32 / F16 / BF16)");
+  if (a->gran < 0) a->gran = default_granularity(a->N, a->d_model, a->h);
+  if (a->gran != QMHA_GRAN_TENSOR && a->gran != QMHA_GRAN_HEAD && a->gran != QMHA_GRAN_BLOCK)
+    return fail("unknown scale granularity");
+  return 0;
+}
+
+int forward_device(const qmha_args& a) {
+  const int dev = require_device();
+  if (dev < 0) return 1;
+  int d, n_pad, d_pad;
+  if (check_shape(a.B, a.N, a.d_model, a.h, &d, &n_pad, &d_pad)) return 1;
+  const size_t units = (size_t)a.B * a.h;
+  const size_t elt = a.kernel == QMHA_KERNEL_INT8 ? 1 : 2;
+  Workspace* w;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, units * n_pad * d_pad * elt, units * n_pad * d_pad * 2,
+                    scale_count((int)units, n_pad, a.gran), &w, &call_lock))
+    return 1;
+  if (fail_on_recorded_stall(w)) return 1;
+  cudaStream_t s = (cudaStream_t)a.stream;
+  WorkspaceUse use;   // orders this call behind earlier work on other streams that uses the workspace
+  use.begin(w, std::move(call_lock), s);
+  if (prepare_impl(w, a.Q, a.K, a.V, a.in_dtype, a.B, a.N, a.d_model, a.h, a.kernel, a.gran,
+                   rope_from(a.rope, a.rope_base), w->Qp, w->Kp, w->Vt, w->scales, w->amax, s))
+    return 1;
+  if (attention_impl(w, w->Qp, w->Kp, w->Vt, w->scales, a.O, a.out_dtype, a.B, a.N, a.d_model, a.h, a.kernel, s,
+                     nullptr, a.variant, a.gran, w->aux, w->vmax))
+    return 1;
+  g_err.clear();
+  return 0;
+}
+
+qmha_args make_args(const void* Q, const void* K, const void* V, void* O, int B, int N, int d_model, int h,
+                    int kernel, int gran, void* stream) {
+  qmha_args a;
+  memset(&a, 0, sizeof(a));
+  a.struct_size = sizeof(a);
+  a.Q = Q; a.K = K; a.V = V; a.O = O;
+  a.B = B; a.N = N; a.d_model = d_model; a.h = h;
+  a.kernel = kernel; a.gran = gran;
+  a.in_dtype = a.out_dtype = QMHA_DTYPE_F32;
+  a.rope = -1; a.rope_base = 0.f; a.variant = -1;
+  a.stream = stream;
+  return a;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* qmha_last_error(void) { return g_err.c_str(); }
-const char* qmha_version(void) { return "quantizedmha_b200 0.1 (sm_100a)"; }
+const char* qmha_version(void) { return "quantizedmha_b200 0.2 (sm_100a)"; }
 int64_t qmha_launch_count(void) { return g_launches.load(); }
 
 int qmha_kernel_from_name(const char* name) {
@@ -341,35 +487,34 @@ int qmha_kernel_from_name(const char* name) {
       n == "fa_tc_v1a" || n == "fa_tc_v1b" || n == "fa_tc_v2" || n == "fa_tc_v2a" ||
       n == "fa_tc_v2b" || n == "fa_tc" || n == "fa_warps")
     return QMHA_KERNEL_F16;
+  if (n == "bf16" || n == "fa_b200_bf16") return QMHA_KERNEL_BF16;
   return -1;
 }
 
 int qmha_set_kernel(const char* name) {
   int k = qmha_kernel_from_name(name);
   if (k < 0) return fail(std::string("unknown kernel name: ") + (name ? name : "(null)"));
-  g_default_kernel = k;
+  g_default_kernel.store(k);
   g_err.clear();
   return 0;
 }
 
 int qmha_set_rope(int enable, float base) {
   if (enable && !(base > 1.0f)) return fail("rope base must be > 1");
-  g_rope = enable ? 1 : 0;
-  if (enable) g_rope_base = base;
+  if (enable) g_rope_base.store(base);
+  g_rope.store(enable ? 1 : 0);
   g_err.clear();
   return 0;
 }
-int qmha_get_rope(void) { return rope_enabled() ? 1 : 0; }
+int qmha_get_rope(void) { return rope_default() ? 1 : 0; }
 
-int qmha_default_granularity(int d_model, int h) {
-  const char* env = getenv("QMHA_SCALES");
-  if (env && !strcmp(env, "head")) return QMHA_GRAN_HEAD;
-  if (env && !strcmp(env, "tensor")) return QMHA_GRAN_TENSOR;
-  if (h > 0 && d_model % h == 0 && ((d_model / h) & 3) == 0) return QMHA_GRAN_BLOCK;
-  return QMHA_GRAN_HEAD;
+int qmha_default_granularity(int d_model, int h) { return default_granularity(0, d_model, h); }
+int qmha_granularity_for(int N, int d_model, int h) { return default_granularity(N, d_model, h); }
+
+const char* qmha_get_kernel(void) {
+  const int k = resolve_default_kernel();
+  return k == QMHA_KERNEL_INT8 ? "int8" : (k == QMHA_KERNEL_BF16 ? "bf16" : "f16");
 }
-
-const char* qmha_get_kernel(void) { return resolve_default_kernel() == QMHA_KERNEL_INT8 ? "int8" : "f16"; }
 
 int qmha_workspace_dims(int N, int d_model, int h, int* n_pad, int* d_pad) {
   int d, np, dp;
@@ -383,6 +528,12 @@ int qmha_workspace_dims(int N, int d_model, int h, int* n_pad, int* d_pad) {
 int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int N, int d_model,
                       int h, int gran, int8_t* Qp, int8_t* Kp, uint16_t* Vt, float* scales,
                       void* stream) {
+  return qmha_quantize_qkv_ex(Q, K, V, QMHA_DTYPE_F32, B, N, d_model, h, gran, -1, 0.f, Qp, Kp, Vt, scales, stream);
+}
+
+int qmha_quantize_qkv_ex(const void* Q, const void* K, const void* V, int in_dtype, int B, int N, int d_model,
+                         int h, int gran, int rope, float rope_base, int8_t* Qp, int8_t* Kp, uint16_t* Vt,
+                         float* scales, void* stream) {
   const int dev = require_device();
   if (dev < 0) return 1;
   if (gran != QMHA_GRAN_TENSOR && gran != QMHA_GRAN_HEAD && gran != QMHA_GRAN_BLOCK) return fail("unknown scale granularity");
@@ -391,8 +542,24 @@ int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int
   if (get_workspace(dev, 0, 0, (size_t)3 * B * h, &w, &call_lock)) return 1;
   WorkspaceUse use;
   use.begin(w, std::move(call_lock), (cudaStream_t)stream);
-  if (prepare_impl(Q, K, V, B, N, d_model, h, QMHA_KERNEL_INT8, gran, Qp, Kp, Vt, scales, w->amax,
-                   (cudaStream_t)stream))
+  if (prepare_impl(w, Q, K, V, in_dtype, B, N, d_model, h, QMHA_KERNEL_INT8, gran, rope_from(rope, rope_base),
+                   Qp, Kp, Vt, scales, w->amax, (cudaStream_t)stream))
+    return 1;
+  g_err.clear();
+  return 0;
+}
+
+int qmha_convert_qkv_16(const void* Q, const void* K, const void* V, int in_dtype, int B, int N, int d_model,
+                        int h, int kernel, int rope, float rope_base, uint16_t* Qp, uint16_t* Kp, uint16_t* Vt,
+                        void* stream) {
+  const int dev = require_device();
+  if (dev < 0) return 1;
+  if (kernel != QMHA_KERNEL_F16 && kernel != QMHA_KERNEL_BF16) return fail("qmha_convert_qkv_16: kernel must be F16 or BF16");
+  Workspace* w;   // the call lock guards the rope table cache
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 0, 0, 0, &w, &call_lock)) return 1;
+  if (prepare_impl(w, Q, K, V, in_dtype, B, N, d_model, h, kernel, QMHA_GRAN_HEAD, rope_from(rope, rope_base),
+                   Qp, Kp, Vt, nullptr, nullptr, (cudaStream_t)stream))
     return 1;
   g_err.clear();
   return 0;
@@ -400,22 +567,15 @@ int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int
 
 int qmha_convert_qkv_f16(const float* Q, const float* K, const float* V, int B, int N, int d_model,
                          int h, uint16_t* Qp, uint16_t* Kp, uint16_t* Vt, void* stream) {
-  if (require_device() < 0) return 1;
-  if (prepare_impl(Q, K, V, B, N, d_model, h, QMHA_KERNEL_F16, QMHA_GRAN_HEAD, Qp, Kp, Vt, nullptr,
-                   nullptr, (cudaStream_t)stream))
-    return 1;
-  g_err.clear();
-  return 0;
+  return qmha_convert_qkv_16(Q, K, V, QMHA_DTYPE_F32, B, N, d_model, h, QMHA_KERNEL_F16, -1, 0.f, Qp, Kp, Vt, stream);
 }
 
 int qmha_quantize_blocks(const float* X, int B, int N, int d_model, int h, int block_rows,
                          int8_t* q, float* scales, void* stream) {
   if (require_device() < 0) return 1;
-  int d, n_pad, d_pad;
   if (B < 1 || N < 1 || h < 1 || d_model % h != 0 || block_rows < 1)
     return fail("invalid shape for qmha_quantize_blocks");
-  (void)n_pad; (void)d_pad;
-  d = d_model / h;
+  const int d = d_model / h;
   cudaError_t e = qmha::launch_quantize_blocks(X, B, N, h, d, block_rows, q, scales,
                                                (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("quantize_blocks launch", e);
@@ -438,18 +598,25 @@ int qmha_quantize_static(const float* X, int64_t n, float scale, float zero_poin
 int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt, const float* scales,
                             float* O, int B, int N, int d_model, int h, int kernel, int gran,
                             void* stream) {
+  return qmha_attention_prepared_ex(Qp, Kp, Vt, scales, O, QMHA_DTYPE_F32, B, N, d_model, h, kernel, gran, stream);
+}
+
+int qmha_attention_prepared_ex(const void* Qp, const void* Kp, const uint16_t* Vt, const float* scales,
+                               void* O, int out_dtype, int B, int N, int d_model, int h, int kernel, int gran,
+                               void* stream) {
   const int dev = require_device();
   if (dev < 0) return 1;
-  if (kernel != QMHA_KERNEL_INT8 && kernel != QMHA_KERNEL_F16) return fail("unknown kernel id");
+  if (!kernel_ok(kernel)) return fail("unknown kernel id");
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   Workspace* w;
   std::unique_lock<std::mutex> call_lock;
   if (get_workspace(dev, 0, 0, scale_count(B * h, n_pad, gran), &w, &call_lock)) return 1;
+  if (fail_on_recorded_stall(w)) return 1;
   WorkspaceUse use;
   use.begin(w, std::move(call_lock), (cudaStream_t)stream);
-  if (attention_impl(Qp, Kp, Vt, scales, O, B, N, d_model, h, kernel, w->error_flag,
-                     (cudaStream_t)stream, nullptr, -1, gran, w->aux, w->vmax, w->cycles))
+  if (attention_impl(w, Qp, Kp, Vt, scales, O, out_dtype, B, N, d_model, h, kernel, (cudaStream_t)stream,
+                     nullptr, -1, gran, w->aux, w->vmax, w->cycles))
     return 1;
   g_err.clear();
   return 0;
@@ -457,28 +624,24 @@ int qmha_attention_prepared(const void* Qp, const void* Kp, const uint16_t* Vt, 
 
 int qmha_forward(const float* Q, const float* K, const float* V, float* O, int B, int N,
                  int d_model, int h, int kernel, int gran, void* stream) {
-  const int dev = require_device();
-  if (dev < 0) return 1;
-  if (kernel != QMHA_KERNEL_INT8 && kernel != QMHA_KERNEL_F16) return fail("unknown kernel id");
-  int d, n_pad, d_pad;
-  if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
-  const size_t units = (size_t)B * h;
-  const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
-  Workspace* w;
-  std::unique_lock<std::mutex> call_lock;
-  if (get_workspace(dev, units * n_pad * d_pad * elt, units * n_pad * d_pad * 2,
-                    scale_count((int)units, n_pad, gran), &w, &call_lock))
-    return 1;
-  cudaStream_t s = (cudaStream_t)stream;
-  WorkspaceUse use;   // orders this call behind earlier work on other streams that uses the workspace
-  use.begin(w, std::move(call_lock), s);
-  if (prepare_impl(Q, K, V, B, N, d_model, h, kernel, gran, w->Qp, w->Kp, w->Vt, w->scales, w->amax, s))
-    return 1;
-  if (attention_impl(w->Qp, w->Kp, w->Vt, w->scales, O, B, N, d_model, h, kernel, w->error_flag, s,
-                     nullptr, -1, gran, w->aux, w->vmax))
-    return 1;
-  g_err.clear();
-  return 0;
+  qmha_args a = make_args(Q, K, V, O, B, N, d_model, h, kernel, gran, stream);
+  if (!kernel_ok(kernel)) return fail("unknown kernel id");
+  if (resolve_args(&a)) return 1;
+  return forward_device(a);
+}
+
+int qmha_forward_ex(const qmha_args* args) {
+  if (!args) return fail("qmha_forward_ex: null argument block");
+  if (args->struct_size != sizeof(qmha_args))
+    return fail("qmha_forward_ex: struct_size does not match this library's qmha_args (header / library mismatch)");
+  qmha_args a = *args;
+  if (resolve_args(&a)) return 1;
+  return forward_device(a);
+}
+
+void qmha_args_init(qmha_args* a) {
+  if (!a) return;
+  *a = make_args(nullptr, nullptr, nullptr, nullptr, 1, 0, 0, 0, -1, -1, nullptr);
 }
 
 // Debug: runs the traced INT8 d=128 kernel once (synchronously) and copies the timeline of CTA
@@ -499,7 +662,7 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
   cudaError_t e = cudaMalloc(&dtrace, n * sizeof(long long));
   if (e != cudaSuccess) return fail_cuda("cudaMalloc(trace)", e);
   cudaMemset(dtrace, 0, n * sizeof(long long));
-  int rc = attention_impl(Qp, Kp, Vt, scales, O, B, N, d_model, h, QMHA_KERNEL_INT8, w->error_flag,
+  int rc = attention_impl(w, Qp, Kp, Vt, scales, O, QMHA_DTYPE_F32, B, N, d_model, h, QMHA_KERNEL_INT8,
                           nullptr, dtrace, variant);
   if (rc == 0) {
     e = cudaDeviceSynchronize();
@@ -527,7 +690,22 @@ int qmha_debug_cycles(unsigned long long* out2, int reset) {
   return 0;
 }
 
-// Checks the asynchronous failure flag of the current device after the caller synchronised.
+// Test hook: plants a failure record exactly as a stalled CTA would (device flag of a launch id that is
+// never used + the mapped host word), so the host-side reporting can be exercised without a hung kernel.
+int qmha_debug_inject_stall(int site) {
+  const int dev = require_device();
+  if (dev < 0) return 1;
+  Workspace* w;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 0, 0, 0, &w, &call_lock)) return 1;
+  const int flag = (int)((0xFFFFFu << 12) | (unsigned)(site & 0xFFF));
+  cudaMemcpy(w->error_flag, &flag, sizeof(int), cudaMemcpyHostToDevice);
+  if (w->error_host) *(volatile int*)w->error_host = site & 0xFFF;
+  g_err.clear();
+  return 0;
+}
+
+// Checks the asynchronous failure record of the current device after the caller synchronised.
 int qmha_check_async_error(void) {
   const int dev = require_device();
   if (dev < 0) return 1;
@@ -539,90 +717,114 @@ int qmha_check_async_error(void) {
   return 0;
 }
 
+// Waits for `stream` and reports a pipeline failure of the launches that ran on it.
+int qmha_synchronize(void* stream) {
+  if (require_device() < 0) return 1;
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("qmha_synchronize", e);
+  return qmha_check_async_error();
+}
+
 void solve(const float* Q, const float* K, const float* V, float* output, int N, int d_model,
            int h) {
   // Synchronous on return like the reference (launchers.h:64); errors are recorded, reported on
   // stderr and queryable with qmha_last_error() — solve() itself stays void.
-  const int kernel = resolve_default_kernel();
   // Scales at the reference's own granularity (one per 32-row tile, fa_tc_int8_b.cu:484-518) when the
-  // head dimension allows the vectorised single-pass quantiser, per (batch, head) otherwise.
-  int rc = qmha_forward(Q, K, V, output, 1, N, d_model, h, kernel, qmha_default_granularity(d_model, h), nullptr);
-  if (rc == 0) {
-    cudaError_t e = cudaStreamSynchronize(nullptr);
-    if (e != cudaSuccess) rc = fail_cuda("solve", e);
-    else rc = qmha_check_async_error();
-  }
+  // head dimension allows the vectorised single-pass quantiser and the sequence fits the per-block table,
+  // per (batch, head) otherwise.
+  int rc = qmha_forward(Q, K, V, output, 1, N, d_model, h, resolve_default_kernel(), -1, nullptr);
+  if (rc == 0) rc = qmha_synchronize(nullptr);
   if (rc != 0) fprintf(stderr, "qmha solve() failed: %s\n", g_err.c_str());
 }
 
+// Host buffers in, host buffer out.  The work is cut into (batch entry, head group) chunks — the reference's
+// own call shape is B = 1, so batch entries alone would leave nothing to overlap — and chunk c+1's H2D copy
+// overlaps chunk c's kernels and chunk c-1's D2H copy: kHostSlots staging slots, each with its own stream;
+// a head group is a strided 2-D region of the [N, d_model] matrices (cudaMemcpy2DAsync), compact on the device.
 int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, int B, int N,
                       int d_model, int h, int kernel, int gran) {
   const int dev = require_device();
   if (dev < 0) return 1;
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
+  if (!kernel_ok(kernel)) return fail("unknown kernel id");
+  if (gran < 0) gran = default_granularity(N, d_model, h);
   if (kernel == QMHA_KERNEL_INT8 && gran == QMHA_GRAN_TENSOR)
-    return fail("qmha_forward_host pipelines over batches; use QMHA_GRAN_HEAD scales");
-  // Pipeline over batch entries: H2D(b+1) overlaps compute(b) overlaps D2H(b-1).  Two slots of
-  // device staging; each slot has its own stream so copies and kernels of different slots overlap.
-  struct Slot { float *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr; cudaStream_t s = nullptr; };
-  static std::map<int, std::pair<size_t, std::vector<Slot>>> staging;  // per device
-  const size_t slab = (size_t)N * d_model;  // elements per batch entry
-  cudaError_t e;
-  std::vector<Slot>* slots;
-  // Each slot needs its own operand workspace region: the slot streams run against disjoint halves.
-  // The workspace's call lock is held for the whole (synchronous) call: it also guards the staging slots.
-  const size_t units1 = (size_t)h;
-  const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
-  const size_t qk1 = units1 * n_pad * d_pad * elt, vt1 = units1 * n_pad * d_pad * 2;
-  const size_t sc1 = scale_count((int)units1, n_pad, gran);
-  Workspace* w;
-  std::unique_lock<std::mutex> call_lock;
-  if (get_workspace(dev, 2 * qk1, 2 * vt1, 2 * sc1, &w, &call_lock)) return 1;
+    return fail("qmha_forward_host pipelines over (batch, head group) chunks; use QMHA_GRAN_HEAD or QMHA_GRAN_BLOCK scales");
+  // Head groups: enough chunks to overlap copies with compute (>= 4 per call when the heads allow it), rows of
+  // at least 512 bytes per 2-D copy line, at most ~64 MB of input per tensor and chunk.
+  int hg = h;
   {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto& st = staging[dev];
-    if (st.second.empty()) st.second.resize(2);
-    if (st.first < slab) {
-      cudaDeviceSynchronize();
-      for (auto& sl : st.second) {
-        cudaFree(sl.q); cudaFree(sl.k); cudaFree(sl.v); cudaFree(sl.o);
-        sl.q = sl.k = sl.v = sl.o = nullptr;
-        if ((e = cudaMalloc(&sl.q, slab * 4)) != cudaSuccess || (e = cudaMalloc(&sl.k, slab * 4)) != cudaSuccess ||
-            (e = cudaMalloc(&sl.v, slab * 4)) != cudaSuccess || (e = cudaMalloc(&sl.o, slab * 4)) != cudaSuccess)
-          return fail_cuda("cudaMalloc(staging)", e);
-        if (!sl.s && (e = cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking)) != cudaSuccess)
-          return fail_cuda("cudaStreamCreate", e);
-      }
-      st.first = slab;
+    const size_t head_bytes = (size_t)N * d * 4;
+    const int min_heads = std::max(1, (int)((512 + d * 4 - 1) / (d * 4)));
+    int want_chunks = std::max(1, (4 + B - 1) / B);                       // per batch entry
+    int by_chunks = std::max(1, h / want_chunks);
+    int by_bytes = std::max(1, (int)((size_t)64 * 1024 * 1024 / std::max<size_t>(head_bytes, 1)));
+    hg = std::max(min_heads, std::min(by_chunks, by_bytes));
+    hg = std::min(hg, h);
+    while (h % hg != 0) --hg;   // equal groups keep one operand layout per slot
+    const char* env = getenv("QMHA_HOST_HEAD_GROUP");
+    if (env && atoi(env) > 0 && h % atoi(env) == 0) hg = atoi(env);
+  }
+  const int groups = h / hg;
+  const int dmg = hg * d;                         // d_model of one chunk on the device
+  const size_t chunk = (size_t)N * dmg;           // elements per tensor and chunk
+  const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
+  const size_t qk1 = (size_t)hg * n_pad * d_pad * elt, vt1 = (size_t)hg * n_pad * d_pad * 2;
+  const size_t sc1 = scale_count(hg, n_pad, gran);
+  Workspace* w;
+  std::unique_lock<std::mutex> call_lock;   // held for the whole (synchronous) call: it also guards the slots
+  // (+32 per slot: the per-head quantiser's queue scratch is 16 + 6 * units words per slot, see amax below)
+  if (get_workspace(dev, kHostSlots * qk1, kHostSlots * vt1, kHostSlots * (sc1 + 32), &w, &call_lock)) return 1;
+  if (fail_on_recorded_stall(w)) return 1;
+  cudaError_t e;
+  if (w->host_slot_elems < chunk) {
+    cudaDeviceSynchronize();
+    w->host_slot_elems = 0;
+    for (HostSlot& sl : w->host_slots) {
+      cudaFree(sl.q); cudaFree(sl.k); cudaFree(sl.v); cudaFree(sl.o);
+      sl.q = sl.k = sl.v = sl.o = nullptr;
     }
-    slots = &st.second;
+    for (HostSlot& sl : w->host_slots) {
+      if ((e = cudaMalloc(&sl.q, chunk * 4)) != cudaSuccess || (e = cudaMalloc(&sl.k, chunk * 4)) != cudaSuccess ||
+          (e = cudaMalloc(&sl.v, chunk * 4)) != cudaSuccess || (e = cudaMalloc(&sl.o, chunk * 4)) != cudaSuccess)
+        return fail_cuda("cudaMalloc(staging)", e);   // host_slot_elems stays 0: the next call starts over
+      if (!sl.s && (e = cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail_cuda("cudaStreamCreate", e);
+    }
+    w->host_slot_elems = chunk;
   }
   // earlier asynchronous calls (qmha_forward on a caller stream) may still be using the workspace
   if (w->in_flight)
-    for (auto& sl : *slots) cudaStreamWaitEvent(sl.s, w->last_use, 0);
+    for (HostSlot& sl : w->host_slots) cudaStreamWaitEvent(sl.s, w->last_use, 0);
+  const RopeOpt rope = rope_from(-1, 0.f);
+  const size_t pitch_host = (size_t)d_model * 4, width = (size_t)dmg * 4;
+  int c = 0;
   for (int b = 0; b < B; ++b) {
-    Slot& sl = (*slots)[b & 1];
-    const size_t off = (size_t)b * slab;
-    const int half = b & 1;
-    // stream order on sl.s serialises reuse of this slot (b-2's D2H precedes b's H2D).
-    if ((e = cudaMemcpyAsync(sl.q, Q + off, slab * 4, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(sl.k, K + off, slab * 4, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(sl.v, V + off, slab * 4, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess)
-      return fail_cuda("H2D copy", e);
-    void* Qp = (char*)w->Qp + half * qk1;
-    void* Kp = (char*)w->Kp + half * qk1;
-    void* Vt = (char*)w->Vt + half * vt1;
-    float* sc = w->scales + half * sc1;
-    unsigned* am = w->amax + half * sc1;
-    if (prepare_impl(sl.q, sl.k, sl.v, 1, N, d_model, h, kernel, gran, Qp, Kp, Vt, sc, am, sl.s)) return 1;
-    if (attention_impl(Qp, Kp, Vt, sc, sl.o, 1, N, d_model, h, kernel, w->error_flag, sl.s, nullptr, -1,
-                       gran, w->aux + half * sc1, w->vmax + half * sc1))
-      return 1;
-    if ((e = cudaMemcpyAsync(O + off, sl.o, slab * 4, cudaMemcpyDeviceToHost, sl.s)) != cudaSuccess)
-      return fail_cuda("D2H copy", e);
+    for (int g = 0; g < groups; ++g, ++c) {
+      const int si = c % kHostSlots;
+      HostSlot& sl = w->host_slots[si];
+      const size_t off = (size_t)b * N * d_model + (size_t)g * dmg;
+      // stream order on sl.s serialises the reuse of this slot (chunk c-kHostSlots' D2H precedes c's H2D)
+      if ((e = cudaMemcpy2DAsync(sl.q, width, Q + off, pitch_host, width, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess ||
+          (e = cudaMemcpy2DAsync(sl.k, width, K + off, pitch_host, width, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess ||
+          (e = cudaMemcpy2DAsync(sl.v, width, V + off, pitch_host, width, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess)
+        return fail_cuda("H2D copy", e);
+      void* Qp = (char*)w->Qp + si * qk1;
+      void* Kp = (char*)w->Kp + si * qk1;
+      void* Vt = (char*)w->Vt + si * vt1;
+      float* sc = w->scales + si * sc1;
+      unsigned* am = w->amax + si * (2 * sc1 + 64);
+      if (prepare_impl(w, sl.q, sl.k, sl.v, QMHA_DTYPE_F32, 1, N, dmg, hg, kernel, gran, rope, Qp, Kp, Vt, sc, am, sl.s))
+        return 1;
+      if (attention_impl(w, Qp, Kp, Vt, sc, sl.o, QMHA_DTYPE_F32, 1, N, dmg, hg, kernel, sl.s, nullptr, -1, gran,
+                         w->aux + si * sc1, w->vmax + si * sc1))
+        return 1;
+      if ((e = cudaMemcpy2DAsync(O + off, pitch_host, sl.o, width, width, N, cudaMemcpyDeviceToHost, sl.s)) != cudaSuccess)
+        return fail_cuda("D2H copy", e);
+    }
   }
-  for (auto& sl : *slots)
+  for (HostSlot& sl : w->host_slots)
     if ((e = cudaStreamSynchronize(sl.s)) != cudaSuccess) return fail_cuda("forward_host sync", e);
   w->in_flight = false;   // everything that used the workspace, this call's and earlier work, has completed
   if (check_error_flag(w)) return 1;
@@ -637,8 +839,16 @@ void qmha_shutdown(void) {
   for (auto& kv : g_ws) {
     cudaSetDevice(kv.first);
     Workspace& w = kv.second;
+    cudaDeviceSynchronize();
     cudaFree(w.Qp); cudaFree(w.Kp); cudaFree(w.Vt); cudaFree(w.scales); cudaFree(w.amax); cudaFree(w.aux); cudaFree(w.vmax);
-    cudaFree(w.error_flag); cudaFree(w.rope_tab); cudaFree(w.cycles);
+    cudaFree(w.error_flag); cudaFree(w.cycles);
+    if (w.error_host) cudaFreeHost(w.error_host);
+    for (auto& t : w.rope) cudaFree(t.second.dev);
+    for (float2* p : w.rope_retired) cudaFree(p);
+    for (HostSlot& sl : w.host_slots) {
+      cudaFree(sl.q); cudaFree(sl.k); cudaFree(sl.v); cudaFree(sl.o);
+      if (sl.s) cudaStreamDestroy(sl.s);
+    }
     if (w.last_use) cudaEventDestroy(w.last_use);
   }
   g_ws.clear();

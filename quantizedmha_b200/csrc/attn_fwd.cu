@@ -115,6 +115,9 @@ struct Cfg {
       kInt8 ? make_idesc(kAccS32, kFmtS8, kFmtS8, kBM, kHN)
             : make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kHN);
   static constexpr uint32_t kIdescPV = make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kD);
+  // BF16 anchor: same kind::f16 instructions with the bf16 operand format (operands, P and V^T are bf16)
+  static constexpr uint32_t kIdescQKbf = make_idesc(kAccF32, kFmtBF16, kFmtBF16, kBM, kHN);
+  static constexpr uint32_t kIdescPVbf = make_idesc(kAccF32, kFmtBF16, kFmtBF16, kBM, kD);
 };
 
 struct Barriers {
@@ -133,7 +136,24 @@ static_assert(sizeof(Barriers) <= 512, "barrier block too large");
 // Bounded mbarrier wait.  A healthy wait is microseconds; after ~1e9 cycles (or as soon as any
 // CTA has raised the global error flag) the wait gives up, records the site and lets the CTA
 // drain so the kernel always terminates and the host can report the failure.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int site,
+// Failure record of one launch.  flag = (launch id << 12) | wait site: a failure only drains the CTAs of the
+// launch that raised it (an earlier version used a bare site number, which made every LATER launch return at
+// kernel entry with its output unwritten); `host` is a mapped host word the library checks at the start of
+// every call without synchronising.
+struct ErrCtx {
+  int* flag;
+  int* host;
+  unsigned id;
+  __device__ __forceinline__ bool raised() const {
+    return ((unsigned)*((volatile int*)flag) >> 12) == id;
+  }
+  __device__ __forceinline__ void raise(int site) const {
+    atomicExch(flag, (int)((id << 12) | (unsigned)site));
+    if (host) { *((volatile int*)host) = site; __threadfence_system(); }
+  }
+};
+
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, const ErrCtx& err_flag, int site,
                                           bool& dead) {
   if (dead) return false;
   if (mbar_try_wait(bar, parity)) return true;
@@ -144,8 +164,8 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
 #endif
   while (!mbar_try_wait_hint(bar, parity, QMHA_WAIT_HINT_NS)) {
     if ((++spins & 0xFu) == 0) {
-      if (clock64() - t0 > 1000000000LL || *((volatile int*)err_flag) != 0) {
-        atomicCAS(err_flag, 0, site);
+      if (clock64() - t0 > 1000000000LL || err_flag.raised()) {
+        if (!err_flag.raised()) err_flag.raise(site);
         dead = true;
         return false;
       }
@@ -312,7 +332,7 @@ __device__ __forceinline__ void i2f_pair(uint32_t s0, uint32_t s1, int one, int 
 }
 
 // kPolyEvery: every kPolyEvery-th pair of the row takes the polynomial path (0 = all on MUFU).
-template <bool kInt8, bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2>
+template <bool kInt8, bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2, bool kBf16 = false>
 __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t (&p)[kHN / 2],
                                              float c, float m_used, int n_valid,
                                              uint64_t (&lsum)[2], int one) {
@@ -342,7 +362,7 @@ __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t 
       if (2 * i + 1 >= n_valid) e1 = 0.f;
     }
     if (!(QMHA_KO & 2)) lsum[i & 1] = fadd2(lsum[i & 1], pack2(e0, e1));
-    p[i] = (QMHA_KO & 1) ? __float_as_uint(e0) : pack_f16x2(e0, e1);
+    p[i] = (QMHA_KO & 1) ? __float_as_uint(e0) : (kBf16 ? pack_bf16x2(e0, e1) : pack_f16x2(e0, e1));
   }
 }
 
@@ -412,7 +432,7 @@ __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint3
   }
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25, bool kBf16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -420,6 +440,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   using C = Cfg<kInt8, kD>;
   constexpr bool kSoftRing = QMHA_SOFT_RING == 2 || (QMHA_SOFT_RING == 1 && !kInt8);
   constexpr bool kLazyPv = QMHA_LAZY_PV == 2 || (QMHA_LAZY_PV == 1 && !kInt8);
+  static_assert(!kBf16 || !kInt8, "bf16 is a variant of the 16-bit kernel");
+  constexpr uint32_t kIdQK = kBf16 ? C::kIdescQKbf : C::kIdescQK;
+  constexpr uint32_t kIdPV = kBf16 ? C::kIdescPVbf : C::kIdescPV;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -435,10 +458,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int unit = blockIdx.y;                 // b * H + head
   const int q_base = blockIdx.x * (2 * kBM);   // first query row of this CTA
   const int n_tiles = prm.n_kv_tiles;
-  int* err_flag = prm.error_flag;
+  const ErrCtx err_flag{prm.error_flag, prm.error_host, prm.launch_id};
   bool dead = false;
 
-  if (*((volatile int*)err_flag) != 0) return;  // an earlier CTA already failed: drain the grid
+  if (err_flag.raised()) return;  // an earlier CTA of this launch already failed: drain the grid
   const long long t_entry = (prm.cycles != nullptr && threadIdx.x == 0) ? clock64() : 0;
   // traced build: a CTA from the middle of the run (steady state, warm caches); phase stamps of its
   // warp 0 go behind the per-step stamps: entry, setup done, first scores, last P, O final, stores, exit
@@ -557,8 +580,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint64_t a = advance_smem_desc(a0, off);
           const uint64_t b = advance_smem_desc(b0, off);
           if (do_mma) {
-            if constexpr (kInt8) mma_i8_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
-            else mma_f16_ss(d_tmem, a, b, C::kIdescQK, ks > 0);
+            if constexpr (kInt8) mma_i8_ss(d_tmem, a, b, kIdQK, ks > 0);
+            else mma_f16_ss(d_tmem, a, b, kIdQK, ks > 0);
           }
         }
       };
@@ -570,7 +593,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int ks = 0; ks < C::kStepsPV; ++ks) {
           const uint64_t b = advance_smem_desc(b0, (uint32_t)ks * 32);
-          if (do_mma) mma_f16_ts(d_tmem, p_tmem + ks * 8, b, C::kIdescPV, (accumulate || ks > 0) ? 1u : 0u);
+          if (do_mma) mma_f16_ts(d_tmem, p_tmem + ks * 8, b, kIdPV, (accumulate || ks > 0) ? 1u : 0u);
         }
       };
 
@@ -772,7 +795,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         return;
       }
       if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, kB, kE>(sx, p, k, m_used, kHN, ls, one);
-      else tile_row_exp<kInt8, false, kPolyEvery, kB, kE>(sx, p, c, m_used, kHN, lsum, one);
+      else tile_row_exp<kInt8, false, kPolyEvery, kB, kE, kBf16>(sx, p, c, m_used, kHN, lsum, one);
     };
 
     // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld).  `probed` is the
@@ -920,8 +943,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         else tile_row_exp_blk<false, kPolyEvery>(cur, p, kl, m_used, kHN, ls, one);
         fold_sums(ls, kl);
       } else {
-        if (masked) tile_row_exp<kInt8, true, kPolyEvery>(cur, p, c, m_used, n_valid, lsum, one);
-        else tile_row_exp<kInt8, false, kPolyEvery>(cur, p, c, m_used, kHN, lsum, one);
+        if (masked) tile_row_exp<kInt8, true, kPolyEvery, 0, kHN / 2, kBf16>(cur, p, c, m_used, n_valid, lsum, one);
+        else tile_row_exp<kInt8, false, kPolyEvery, 0, kHN / 2, kBf16>(cur, p, c, m_used, kHN, lsum, one);
       }
       if (tracer) tr[i * 4 + 2] = clock64();
       // P(i) goes over P(i-2).  In the steady state the fetch of S(i+1) proves that P·V(i-2) has
@@ -981,7 +1004,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float inv = (l > 0.f) ? out_scale / l : 0.f;  // fa_tc_int8_b.cu:549-553 guard
     const int row = q_base + t * kBM + row_in_tile;
     const int b = unit / prm.H, head = unit % prm.H;
-    float* out = prm.O + ((size_t)b * prm.N + row) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d;
+    const int osz = prm.out_dtype == 0 ? 4 : 2;   // output element size
+    auto pack16 = [&](float lo, float hi) { return prm.out_dtype == 2 ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi); };
+    char* out_b = reinterpret_cast<char*>(prm.O) +
+                  (((size_t)b * prm.N + row) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d) * osz;
+    float* out = reinterpret_cast<float*>(out_b);
     const bool row_ok = row < prm.N;
     const bool vec_ok = (prm.d & 3) == 0;
     constexpr bool kStaged = C::kTileBytesQK >= 16384;
@@ -1023,11 +1050,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t o[32];
         tmem_ld32(tO + ch * 32, o);
         tmem_wait_ld();
+        if (prm.out_dtype == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 v = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
-                                       __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
-          *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
+                                         __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
+            *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+          }
+        } else {   // 16-bit output: 32 rows x 64 B, SWIZZLE_64B (16-byte chunk index ^= (row >> 1) & 3)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack16(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+            v.y = pack16(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+            v.z = pack16(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+            v.w = pack16(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(reinterpret_cast<char*>(buf) + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = v;
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -1039,13 +1078,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (tracer && warp == 0) phase[11] = clock64();
       if (lane == 0) bulk_wait_group_read<0>();
       __syncwarp();
-    } else if (kStaged && vec_ok) {
+    } else if (kStaged && vec_ok && prm.out_dtype == 0) {
       // Same staging through the (dead) Q tile of this warpgroup, written out with ordinary 16-byte
       // stores: 8 lanes cover one 128-byte row segment, 4 rows per instruction.
       float* stage = reinterpret_cast<float*>(sQ + t * C::kTileBytesQK) + (warp & 3) * 1024;  // 32 x 32 floats
       const int r_sub = lane >> 3, c4 = lane & 7;
       const int row0 = q_base + t * kBM + (warp & 3) * 32;          // first row of this warp
-      float* out0 = prm.O + ((size_t)b * prm.N + row0) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d;
+      float* out0 = reinterpret_cast<float*>(prm.O) + ((size_t)b * prm.N + row0) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d;
       constexpr int kChunks = kD / 32;
       uint32_t o[kChunks][32];
 #pragma unroll
@@ -1076,7 +1115,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t o[32];
         tmem_ld32(tO + ch * 32, o);
         tmem_wait_ld();
-        if (row_ok) {
+        if (row_ok && prm.out_dtype != 0) {   // 16-bit output without TMA: pairs when d is even, scalars otherwise
+          uint16_t* o16 = reinterpret_cast<uint16_t*>(out_b);
+          if ((prm.d & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int col = ch * 32 + i;
+              if (col < prm.d)
+                *reinterpret_cast<uint32_t*>(o16 + col) = pack16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = ch * 32 + i;
+              if (col < prm.d) o16[col] = (uint16_t)(pack16(__uint_as_float(o[i]) * inv, 0.f) & 0xFFFFu);
+            }
+          }
+        } else if (row_ok) {
           if (vec_ok) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -1158,17 +1213,21 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
   return true;
 }
 
-// 3D fp32 tensor [d2][d1][d0] (d0 contiguous), box = [1][box1][box0], SWIZZLE_128B (box0 * 4 == 128).
-bool make_map_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+// 3D output tensor [d2][d1][d0] (d0 contiguous), box = [1][box1][box0]; out_dtype 0 = fp32 (SWIZZLE_128B,
+// box0 * 4 == 128), 1 = fp16 / 2 = bf16 (SWIZZLE_64B, box0 * 2 == 64).
+bool make_map_3d_out(CUtensorMap* m, const void* base, int out_dtype, uint64_t d0, uint64_t d1, uint64_t d2,
                      uint32_t box0, uint32_t box1, std::string* err) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  const uint64_t elt = out_dtype == 0 ? 4 : 2;
   const cuuint64_t gdim[3] = {d0, d1, d2};
-  const cuuint64_t gstride[2] = {d0 * 4, d0 * d1 * 4};
+  const cuuint64_t gstride[2] = {d0 * elt, d0 * d1 * elt};
   const cuuint32_t box[3] = {box0, box1, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapDataType dt = out_dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                               : out_dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(m, dt, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, out_dtype == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     *err = "cuTensorMapEncodeTiled(output) failed with CUresult " + std::to_string((int)r);
@@ -1177,7 +1236,7 @@ bool make_map_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1,
   return true;
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25, bool kBf16 = false>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD>;
   const uint64_t units = (uint64_t)a.B * a.H;
@@ -1190,9 +1249,9 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   CUtensorMap to;
   memset(&to, 0, sizeof(to));
   const bool tma_store = (a.d % 32) == 0 && getenv("QMHA_NO_TMA_STORE") == nullptr;
-  if (tma_store && !make_map_3d_f32(&to, a.O, (uint64_t)a.H * a.d, (uint64_t)a.N, (uint64_t)a.B, 32, 32, err))
+  if (tma_store && !make_map_3d_out(&to, a.O, a.out_dtype, (uint64_t)a.H * a.d, (uint64_t)a.N, (uint64_t)a.B, 32, 32, err))
     return false;
-  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb>;
+  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb, kBf16>;
   // block mode keeps one float4 of constants per 32-key block of the unit behind the barriers
   const size_t smem_bytes = (size_t)C::kSmemBytes + (kBlk ? (size_t)(a.n_pad / 32) * 16 : 0);
   if (smem_bytes > 227 * 1024) {
@@ -1208,6 +1267,9 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.O = a.O;
   p.scales = a.scales;
   p.error_flag = a.error_flag;
+  p.error_host = a.error_host;
+  p.launch_id = a.launch_id;
+  p.out_dtype = a.out_dtype;
   p.trace = a.trace;
   p.blk_scales = a.blk_scales;
   p.blk_aux = a.blk_aux;
@@ -1231,46 +1293,61 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
 
 }  // namespace
 
+int attention_max_block_keys(int d_pad) {
+  const int tiles = d_pad == 32 ? Cfg<true, 32>::kSmemBytes : (d_pad == 64 ? Cfg<true, 64>::kSmemBytes : Cfg<true, 128>::kSmemBytes);
+  return (227 * 1024 - tiles) / 16 * 32;
+}
+
 bool launch_attention(const AttnLaunch& a, std::string* err) {
   if (a.units_y_limit_exceeded()) { *err = "B*h exceeds the CUDA grid.y limit (65535)"; return false; }
   // a.variant = k: exp2 of every k-th score pair goes to the FMA-pipe polynomial (0 = all MUFU)
   const int poly = a.variant;
   const bool blk = a.blk_scales != nullptr;
   if (blk && !a.int8) { *err = "block scales require the INT8 variant"; return false; }
+  if (a.int8 && a.bf16) { *err = "bf16 selects the 16-bit kernel"; return false; }
 #ifndef QMHA_ONLY_D128
   if (a.trace) {
     if (!(a.int8 && a.d_pad == 128)) { *err = "tracing is only built for the INT8 d=128 kernel"; return false; }
     return blk ? launch_cfg<true, 128, 0, true, true>(a, err) : launch_cfg<true, 128, 0, false, true>(a, err);
   }
 #endif
-#ifdef QMHA_ONLY_D128   // quick experiment builds (tools/build_variant.sh): d = 128, all-MUFU exponentials only
-#define QMHA_DISPATCH(INT8, BLK, D)                                   \
-  if (D == 128 && poly == 0) return launch_cfg<INT8, 128, 0, BLK, false>(a, err);
-#else
-#define QMHA_DISPATCH(INT8, BLK, D)                                   \
+#if defined(QMHA_ONLY_D128)   // quick experiment builds (tools/build_variant.sh): d = 128, all-MUFU exponentials only
+#define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
+  if (D == 128 && poly == 0) return launch_cfg<INT8, 128, 0, BLK, false, 6, 25, BF>(a, err);
+#elif defined(QMHA_BUILD_POLY)  // experiment builds with the FMA-pipe exp2 share (measured slower)
+#define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
   switch (poly) {                                                     \
-    case 0: return launch_cfg<INT8, D, 0, BLK, false>(a, err);        \
-    case 4: return launch_cfg<INT8, D, 4, BLK, false>(a, err);        \
-    case 8: return launch_cfg<INT8, D, 8, BLK, false>(a, err);        \
+    case 0: return launch_cfg<INT8, D, 0, BLK, false, 6, 25, BF>(a, err);        \
+    case 4: return launch_cfg<INT8, D, 4, BLK, false, 6, 25, BF>(a, err);        \
+    case 8: return launch_cfg<INT8, D, 8, BLK, false, 6, 25, BF>(a, err);        \
   }
+#else
+#define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
+  if (poly == 0) return launch_cfg<INT8, D, 0, BLK, false, 6, 25, BF>(a, err);
 #endif
   if (a.int8 && blk) {
     switch (a.d_pad) {
-      case 32: QMHA_DISPATCH(true, true, 32) break;
-      case 64: QMHA_DISPATCH(true, true, 64) break;
-      case 128: QMHA_DISPATCH(true, true, 128) break;
+      case 32: QMHA_DISPATCH(true, true, 32, false) break;
+      case 64: QMHA_DISPATCH(true, true, 64, false) break;
+      case 128: QMHA_DISPATCH(true, true, 128, false) break;
     }
   } else if (a.int8) {
     switch (a.d_pad) {
-      case 32: QMHA_DISPATCH(true, false, 32) break;
-      case 64: QMHA_DISPATCH(true, false, 64) break;
-      case 128: QMHA_DISPATCH(true, false, 128) break;
+      case 32: QMHA_DISPATCH(true, false, 32, false) break;
+      case 64: QMHA_DISPATCH(true, false, 64, false) break;
+      case 128: QMHA_DISPATCH(true, false, 128, false) break;
+    }
+  } else if (a.bf16) {
+    switch (a.d_pad) {
+      case 32: QMHA_DISPATCH(false, false, 32, true) break;
+      case 64: QMHA_DISPATCH(false, false, 64, true) break;
+      case 128: QMHA_DISPATCH(false, false, 128, true) break;
     }
   } else {
     switch (a.d_pad) {
-      case 32: QMHA_DISPATCH(false, false, 32) break;
-      case 64: QMHA_DISPATCH(false, false, 64) break;
-      case 128: QMHA_DISPATCH(false, false, 128) break;
+      case 32: QMHA_DISPATCH(false, false, 32, false) break;
+      case 64: QMHA_DISPATCH(false, false, 64, false) break;
+      case 128: QMHA_DISPATCH(false, false, 128, false) break;
     }
   }
 #undef QMHA_DISPATCH

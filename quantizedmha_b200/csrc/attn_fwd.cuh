@@ -7,9 +7,12 @@
 namespace qmha {
 
 struct AttnParams {
-  float* O;             // [B, N, H*d] fp32
+  void* O;              // [B, N, H*d] fp32 / fp16 / bf16 (out_dtype)
   const float* scales;  // [3, units] (INT8 variant) or nullptr
-  int* error_flag;      // device int: 0 = ok, otherwise the wait site that timed out
+  int* error_flag;      // device int: 0 = ok, otherwise (launch id << 12) | wait site that timed out
+  int* error_host;      // mapped host copy of the failing wait site (nullptr = none)
+  unsigned launch_id;   // 20-bit id of this launch (never 0)
+  int out_dtype;        // 0 = fp32, 1 = fp16, 2 = bf16
   const float* blk_scales;  // block mode: [3][units][n_pad/32] raw scales (Q, K, V), else nullptr
   const float* blk_aux;     // block mode: [units][n_pad/32][2] = {log2 r, 1/r}, r = sV_block/sV_max
   const float* blk_vmax;    // block mode: [units] largest V block scale
@@ -31,8 +34,11 @@ struct AttnLaunch {
   const void* Kp;       // [units, n_pad, d_pad]
   const void* Vt;       // [units, d_pad, n_pad] fp16
   const float* scales;
-  float* O;
+  void* O;
+  int out_dtype = 0;    // 0 = fp32, 1 = fp16, 2 = bf16
   int* error_flag;
+  int* error_host = nullptr;
+  unsigned launch_id = 1;
   const float* blk_scales = nullptr;  // non-null selects the per-32-row-block scale kernel (INT8)
   const float* blk_aux = nullptr;
   const float* blk_vmax = nullptr;
@@ -41,9 +47,14 @@ struct AttnLaunch {
   int variant = 0;             // k > 0: exp2 of every k-th score pair on the FMA-pipe polynomial
   int B, N, H, d, n_pad, d_pad;
   bool int8;
+  bool bf16 = false;    // 16-bit kernel with bf16 operands (Qp / Kp / Vt hold bf16)
   cudaStream_t stream;
   bool units_y_limit_exceeded() const { return (long long)B * H > 65535; }
 };
+
+// Longest sequence whose per-32-key-block scale table still fits in shared memory behind the tiles of the
+// INT8 kernel with padded head dimension d_pad (block-scale mode); longer sequences need per-head scales.
+int attention_max_block_keys(int d_pad);
 
 // Enqueues the kernel; returns false and fills *err on a host-side failure.
 bool launch_attention(const AttnLaunch& a, std::string* err);

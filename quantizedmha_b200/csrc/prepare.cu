@@ -18,6 +18,7 @@
 //           quantize_blocks_kernel / quantize_static_kernel -> reference-granularity and
 //           golden-spec (generate_golden.cpp:94-101) quantisers in the input layout.
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "prepare.cuh"
@@ -28,6 +29,41 @@ namespace {
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// Input element types of the extended entry (qmha_forward_ex: fp32 like the reference, or fp16 / bf16 so that
+// 16-bit callers skip the fp32 round trip: 2 instead of 4 bytes read per element).  ld4 = four consecutive
+// elements as fp32 (16-byte / 8-byte read-only load), ld1 = one element.
+template <typename T> struct In;
+template <> struct In<float> {
+  static __device__ __forceinline__ float4 ld4(const float* p) { return ldg_f4(p); }
+  static __device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+};
+template <> struct In<__half> {
+  static __device__ __forceinline__ float4 ld4(const __half* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ float ld1(const __half* p) { return __half2float(__ldg(p)); }
+};
+template <> struct In<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    // bf16 -> fp32 is a 16-bit shift
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                       __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+  }
+  static __device__ __forceinline__ float ld1(const __nv_bfloat16* p) {
+    return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+  }
+};
+// 16-bit operand formats of the attention kernel: kOut 1 = fp16, 2 = bf16 (0 = int8 codes; V codes are fp16)
+template <int kOut>
+__device__ __forceinline__ uint16_t cvt16(float x) {
+  if constexpr (kOut == 2) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  else return __half_as_ushort(__float2half_rn(x));
 }
 
 __device__ __forceinline__ float absmax4(float m, float4 v) {
@@ -89,39 +125,61 @@ __device__ __forceinline__ float4 rope_rotate(float4 x, int vec, int n, int N, i
 constexpr int kAbsmaxThreads = 256;
 constexpr int kAbsmaxRows = 32;
 
+template <typename TIn>
 __global__ void __launch_bounds__(kAbsmaxThreads)
-absmax_kernel(const float* __restrict__ Q, const float* __restrict__ K,
-              const float* __restrict__ V, unsigned* __restrict__ amax_bits, int N, int H, int d) {
+absmax_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
+              const TIn* __restrict__ V, unsigned* __restrict__ amax_bits, int N, int H, int d, int d_pad,
+              const float2* __restrict__ rope) {
   extern __shared__ unsigned s_amax[];  // [H]
   const int z = blockIdx.z, b = blockIdx.y;
-  const float* X = z == 0 ? Q : (z == 1 ? K : V);
+  const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
   const int d_model = H * d;
   const int r0 = blockIdx.x * kAbsmaxRows;
   const int r1 = min(N, r0 + kAbsmaxRows);
   for (int i = threadIdx.x; i < H; i += blockDim.x) s_amax[i] = 0u;
   __syncthreads();
-  const float* base = X + ((size_t)b * N) * d_model;
-  if ((d & 3) == 0) {
+  const TIn* base = X + ((size_t)b * N) * d_model;
+  if (rope != nullptr && z < 2) {
+    // Fused RoPE (per-tensor / two-pass path): the maxima must be those of the ROTATED rows.  Slots are laid
+    // out per head over the padded head dimension (d_pad/4 lanes per head row, a divisor of 32), so the
+    // partner element of the rotation sits in the same warp; the trip count is warp-uniform.
+    const int vpr = d_pad >> 2;
+    const int slots = H * vpr, slots_up = (slots + 31) & ~31;
+    for (int sidx = threadIdx.x; sidx < slots_up; sidx += blockDim.x) {
+      const bool live = sidx < slots;
+      const int head = live ? sidx / vpr : 0;
+      const int vec = live ? sidx % vpr : vpr;          // vpr * 4 >= d: treated as padding by rope_rotate
+      const bool col_ok = live && vec * 4 < d;
+      const TIn* col = base + (size_t)head * d + vec * 4;
+      float m = 0.f;
+      for (int r = r0; r < r1; ++r) {
+        float4 x = col_ok ? In<TIn>::ld4(col + (size_t)r * d_model) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x = rope_rotate(x, vec, r, N, d, rope);
+        m = absmax4(m, x);
+      }
+      if (col_ok) atomicMax(&s_amax[head], __float_as_uint(m));
+    }
+  } else if ((d & 3) == 0) {
     const int vecs = d_model >> 2;
     for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
       const int head = (v << 2) / d;
-      const float* col = base + (size_t)(v << 2);
+      const TIn* col = base + (size_t)(v << 2);
       float m = 0.f;
       int r = r0;
       for (; r + 8 <= r1; r += 8) {
         float4 x[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = ldg_f4(col + (size_t)(r + u) * d_model);
+        for (int u = 0; u < 8; ++u) x[u] = In<TIn>::ld4(col + (size_t)(r + u) * d_model);
 #pragma unroll
         for (int u = 0; u < 8; ++u) m = absmax4(m, x[u]);
       }
-      for (; r < r1; ++r) m = absmax4(m, ldg_f4(col + (size_t)r * d_model));
+      for (; r < r1; ++r) m = absmax4(m, In<TIn>::ld4(col + (size_t)r * d_model));
       atomicMax(&s_amax[head], __float_as_uint(m));
     }
   } else {
     for (int c = threadIdx.x; c < d_model; c += blockDim.x) {
       float m = 0.f;
-      for (int r = r0; r < r1; ++r) m = fmaxf(m, fabsf(__ldg(base + (size_t)r * d_model + c)));
+      for (int r = r0; r < r1; ++r) m = fmaxf(m, fabsf(In<TIn>::ld1(base + (size_t)r * d_model + c)));
       atomicMax(&s_amax[c / d], __float_as_uint(m));
     }
   }
@@ -156,18 +214,19 @@ __global__ void finalize_scales_kernel(const unsigned* __restrict__ amax_bits,
 constexpr int kPrepThreads = 256;
 constexpr int kPrepRows = 128;
 
-template <bool kInt8, int kD>
+template <int kOut, int kD, typename TIn>
 __global__ void __launch_bounds__(kPrepThreads)   // (a six-CTA register budget was measured: no gain)
-prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
-               const float* __restrict__ V, const float* __restrict__ scales, void* __restrict__ Qp,
-               void* __restrict__ Kp, __half* __restrict__ Vt, int N, int H, int d, int n_pad,
+prepare_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
+               const TIn* __restrict__ V, const float* __restrict__ scales, void* __restrict__ Qp,
+               void* __restrict__ Kp, uint16_t* __restrict__ Vt, int N, int H, int d, int n_pad,
                const float2* __restrict__ rope) {
+  constexpr bool kInt8 = kOut == 0;
   const int z = blockIdx.z, unit = blockIdx.y;
   const int b = unit / H, head = unit % H;
   const int n0 = blockIdx.x * kPrepRows;
-  const float* X = z == 0 ? Q : (z == 1 ? K : V);
+  const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
   const int d_model = H * d;
-  const float* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+  const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
   float inv_sc = 1.0f;
   if constexpr (kInt8) inv_sc = 1.0f / scales[(size_t)z * gridDim.y + unit];  // fa_tc_int8_b.cu:106
 
@@ -180,12 +239,12 @@ prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
   auto load4 = [&](int n, int c, float (&x)[4]) {
     x[0] = x[1] = x[2] = x[3] = 0.f;
     if (n < N) {
-      const float* p = src + (size_t)n * d_model + c;
+      const TIn* p = src + (size_t)n * d_model + c;
       if (vec_ok) {
-        if (c < d) { float4 v = ldg_f4(p); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+        if (c < d) { float4 v = In<TIn>::ld4(p); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (c + e < d) x[e] = __ldg(p + e);
+        for (int e = 0; e < 4; ++e) if (c + e < d) x[e] = In<TIn>::ld1(p + e);
       }
     }
   };
@@ -209,18 +268,16 @@ prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                             ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
         *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(dst) + o) = pk;
       } else {
-        __half2 h01 = __floats2half2_rn(x[0], x[1]);
-        __half2 h23 = __floats2half2_rn(x[2], x[3]);
         uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h01);
-        pk.y = *reinterpret_cast<uint32_t*>(&h23);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dst) + o) = pk;
+        pk.x = (uint32_t)cvt16<kOut>(x[0]) | ((uint32_t)cvt16<kOut>(x[1]) << 16);
+        pk.y = (uint32_t)cvt16<kOut>(x[2]) | ((uint32_t)cvt16<kOut>(x[3]) << 16);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dst) + o) = pk;
       }
     }
   } else {
     // V: quantise/convert into a shared tile, then write it transposed (keys contiguous).
     constexpr int kStride = kD + 2;  // halves; odd word stride spreads the transposed reads
-    __shared__ __half tile[kPrepRows * kStride];
+    __shared__ uint16_t tile[kPrepRows * kStride];
     // all loads of the thread are issued before the first conversion (one load in flight per thread
     // leaves HBM idle: this third of the grid ran at ~60 % of the rest)
     constexpr int kIters = kPrepRows / kRowsPerIter;   // 4 / 8 / 16 rows per thread
@@ -237,7 +294,7 @@ prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
         for (int e = 0; e < 4; ++e) {
           float y = x[k][e];
           if constexpr (kInt8) y = (float)quant1(x[k][e], inv_sc);  // int8 code, exact in fp16
-          tile[r * kStride + vec * 4 + e] = __float2half_rn(y);
+          tile[r * kStride + vec * 4 + e] = cvt16<kOut>(y);
         }
       }
     }
@@ -245,8 +302,8 @@ prepare_kernel(const float* __restrict__ Q, const float* __restrict__ K,
     // each thread emits 2 consecutive keys (4 bytes) of one d-row; 64 threads cover 128 keys.
     const int kp = threadIdx.x & 63;
     for (int dd = threadIdx.x >> 6; dd < kD; dd += kPrepThreads / 64) {
-      __half2 o2 = __halves2half2(tile[(2 * kp) * kStride + dd], tile[(2 * kp + 1) * kStride + dd]);
-      *reinterpret_cast<__half2*>(Vt + ((size_t)unit * kD + dd) * n_pad + n0 + 2 * kp) = o2;
+      const uint32_t o2 = (uint32_t)tile[(2 * kp) * kStride + dd] | ((uint32_t)tile[(2 * kp + 1) * kStride + dd] << 16);
+      *reinterpret_cast<uint32_t*>(Vt + ((size_t)unit * kD + dd) * n_pad + n0 + 2 * kp) = o2;
     }
   }
 }
@@ -269,18 +326,18 @@ constexpr int kBlkRows = QMHA_BLKQ_ROWS;
 #ifndef QMHA_BLKQ_CTAS
 #define QMHA_BLKQ_CTAS 6
 #endif
-template <int kD, bool kRope>
+template <int kD, bool kRope, typename TIn>
 __global__ void __launch_bounds__(kPrepThreads, kRope ? 3 : QMHA_BLKQ_CTAS)
-block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
-                      const float* __restrict__ V, float* __restrict__ scales,
+block_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
+                      const TIn* __restrict__ V, float* __restrict__ scales,
                       int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
                       int N, int H, int d, int n_pad, const float2* __restrict__ rope) {
   const int z = blockIdx.z, unit = blockIdx.y;  // (heads-fastest CTA order was measured: no gain)
   const int b = unit / H, head = unit % H;
   const int n0 = blockIdx.x * kBlkRows;
-  const float* X = z == 0 ? Q : (z == 1 ? K : V);
+  const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
   const int d_model = H * d;
-  const float* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+  const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
 
   constexpr int kVecPerRow = kD / 4;
   constexpr int kRowsPerIter = kPrepThreads / kVecPerRow;  // 8 / 16 / 32 rows per pass
@@ -295,7 +352,7 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
 #pragma unroll
   for (int k = 0; k < kLoads; ++k) {
     const int n = n0 + rsub + k * kRowsPerIter;
-    x[k] = (n < N && col_ok) ? ldg_f4(src + (size_t)n * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    x[k] = (n < N && col_ok) ? In<TIn>::ld4(src + (size_t)n * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if constexpr (kRope) {
     if (z < 2) {  // rotate Q and K rows before the block maxima are taken (uniform branch)
@@ -367,13 +424,13 @@ block_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
   }
 }
 
-template <int kD>
+template <int kD, typename TIn>
 cudaError_t launch_block_cfg(const PrepareArgs& a) {
   dim3 grid(a.n_pad / kBlkRows, a.B * a.H, 3);
   // the RoPE variant is a separate instantiation: the plain one stays inside its register budget
-  auto kern = a.rope ? block_quantize_kernel<kD, true> : block_quantize_kernel<kD, false>;
+  auto kern = a.rope ? block_quantize_kernel<kD, true, TIn> : block_quantize_kernel<kD, false, TIn>;
   kern<<<grid, kPrepThreads, 0, a.stream>>>(
-      a.Q, a.K, a.V, a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
+      reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
       reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
   return cudaGetLastError();
 }
@@ -457,10 +514,10 @@ constexpr int kClusterSize = 8;
 constexpr int kFusedThreads = 1024;
 constexpr int kFusedSmemBytes = 120 * 1024;
 
-template <int kD>
+template <int kD, typename TIn>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kFusedThreads, 1)
-fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
-                      const float* __restrict__ V, float* __restrict__ scales,
+fused_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
+                      const TIn* __restrict__ V, float* __restrict__ scales,
                       int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
                       int N, int H, int d, int n_pad, const float2* __restrict__ rope) {
   namespace cg = cooperative_groups;
@@ -472,9 +529,9 @@ fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
   const int z = blockIdx.z, unit = blockIdx.y;
   const int b = unit / H, head = unit % H;
   const int rank = (int)cluster.block_rank();
-  const float* X = z == 0 ? Q : (z == 1 ? K : V);
+  const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
   const int d_model = H * d;
-  const float* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+  const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
 
   // rows of this CTA: a multiple of 128 so V tiles never straddle CTAs
   const int rows_per_cta = ((n_pad / 128 + kClusterSize - 1) / kClusterSize) * 128;
@@ -495,22 +552,22 @@ fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
     // every lane walks the same row slots and loads zeros where it has nothing
     for (int r0 = r_begin; r0 < r_end; r0 += kRowsPerPass) {
       const int r = r0 + rsub;
-      float4 x = (r < N && col_ok) ? ldg_f4(src + (size_t)r * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 x = (r < N && col_ok) ? In<TIn>::ld4(src + (size_t)r * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       x = rope_rotate(x, vec, r, N, d, rope);
       m = absmax4(m, x);
     }
   } else if (col_ok) {
-    const float* col = src + vec * 4;
+    const TIn* col = src + vec * 4;
     int r = r_begin + rsub;
     const int r_stop = min(r_end, N);
     for (; r + 7 * kRowsPerPass < r_stop; r += 8 * kRowsPerPass) {
       float4 x[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = ldg_f4(col + (size_t)(r + u * kRowsPerPass) * d_model);
+      for (int u = 0; u < 8; ++u) x[u] = In<TIn>::ld4(col + (size_t)(r + u * kRowsPerPass) * d_model);
 #pragma unroll
       for (int u = 0; u < 8; ++u) m = absmax4(m, x[u]);
     }
-    for (; r < r_stop; r += kRowsPerPass) m = absmax4(m, ldg_f4(col + (size_t)r * d_model));
+    for (; r < r_stop; r += kRowsPerPass) m = absmax4(m, In<TIn>::ld4(col + (size_t)r * d_model));
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
@@ -536,7 +593,7 @@ fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
   auto load4 = [&](int n, float (&x)[4]) {
     x[0] = x[1] = x[2] = x[3] = 0.f;
     if (n < N && col_ok) {
-      float4 v = ldg_f4(src + (size_t)n * d_model + vec * 4);
+      float4 v = In<TIn>::ld4(src + (size_t)n * d_model + vec * 4);
       x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
     }
   };
@@ -599,26 +656,192 @@ fused_quantize_kernel(const float* __restrict__ Q, const float* __restrict__ K,
   }
 }
 
-template <int kD>
+// ------------------------------------------------------------------------------------------------
+// stream_quantize_kernel: per-(batch, head) scales in ONE launch without clusters.  The cluster kernel above keeps
+// only ~15 slabs in flight and alternates between an HBM phase and an L2 phase per cluster (1.24 ms at the headline
+// shape = 53 % of the HBM roofline).  Here a persistent grid pulls items off one queue ordered as
+//     round r:  absmax of the T 128-row tiles of slab r,  then  quantise + re-layout of the tiles of slab r - kLag
+// so HBM reads (absmax items), L2 re-reads and HBM writes (quantise items) of different slabs overlap all the time,
+// and the re-read of a slab follows its first read by ~kLag slabs of traffic (a few MB: L2 hits).
+// A quantise item waits for the tile counter of its slab; every absmax item of that slab was taken off the queue
+// earlier by a CTA that is running, so the wait always ends.
+//   ctl[0] = queue head;  amax[s], done[s] per slab s = z * units + unit (zeroed by the launcher)
+#ifndef QMHA_STREAM_ROWS
+#define QMHA_STREAM_ROWS 128
+#endif
+#ifndef QMHA_STREAM_LAG
+#define QMHA_STREAM_LAG 2
+#endif
+constexpr int kStreamThreads = 512;
+constexpr int kStreamRows = QMHA_STREAM_ROWS;
+constexpr int kStreamLag = QMHA_STREAM_LAG;
+
+template <int kD, typename TIn>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, const TIn* __restrict__ V,
+                       float* __restrict__ scales, int8_t* __restrict__ Qp, int8_t* __restrict__ Kp,
+                       __half* __restrict__ Vt, unsigned* __restrict__ ctl, unsigned* __restrict__ amax,
+                       unsigned* __restrict__ done, int N, int H, int d, int n_pad, int units,
+                       const float2* __restrict__ rope) {
+  constexpr int kVecPerRow = kD / 4;
+  constexpr int kRowsPerIter = kStreamThreads / kVecPerRow;   // 16 / 32 / 64 rows per pass
+  constexpr int kLoads = kStreamRows / kRowsPerIter;           // 8 / 4 / 2 float4 per thread
+  constexpr int kStride = kD + 2;
+  __shared__ __half tile[kStreamRows * kStride];
+  __shared__ float s_warp_max[kStreamThreads / 32];
+  __shared__ unsigned s_item;
+  const int T = n_pad / kStreamRows;
+  const int slabs = 3 * units;
+  const unsigned total = (unsigned)(slabs + kStreamLag) * 2u * (unsigned)T;
+  const int vec = threadIdx.x % kVecPerRow;
+  const int rsub = threadIdx.x / kVecPerRow;
+  const bool col_ok = vec * 4 < d;
+  const int d_model = H * d;
+  for (;;) {
+    __syncthreads();   // s_item / tile / s_warp_max of the previous item are no longer read
+    if (threadIdx.x == 0) s_item = atomicAdd(&ctl[0], 1u);
+    __syncthreads();
+    const unsigned item = s_item;
+    if (item >= total) break;
+    const int round = (int)(item / (2u * T)), j = (int)(item % (2u * T));
+    const bool quant = j >= T;
+    const int slab = quant ? round - kStreamLag : round;
+    if (slab < 0 || slab >= slabs) continue;
+    const int t = quant ? j - T : j;
+    const int z = slab / units, unit = slab % units;
+    const int b = unit / H, head = unit % H;
+    const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
+    const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+    const int n0 = t * kStreamRows;
+    float4 x[kLoads];
+#pragma unroll
+    for (int k = 0; k < kLoads; ++k) {
+      const int n = n0 + rsub + k * kRowsPerIter;
+      x[k] = (n < N && col_ok) ? In<TIn>::ld4(src + (size_t)n * d_model + vec * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (rope != nullptr && z < 2) {
+#pragma unroll
+      for (int k = 0; k < kLoads; ++k) x[k] = rope_rotate(x[k], vec, n0 + rsub + k * kRowsPerIter, N, d, rope);
+    }
+    if (!quant) {
+      float m = 0.f;
+#pragma unroll
+      for (int k = 0; k < kLoads; ++k) m = absmax4(m, x[k]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      if ((threadIdx.x & 31) == 0) s_warp_max[threadIdx.x >> 5] = m;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        float w = threadIdx.x < kStreamThreads / 32 ? s_warp_max[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, off));
+        if (threadIdx.x == 0) {
+          atomicMax(&amax[slab], __float_as_uint(w));
+          __threadfence();
+          atomicAdd(&done[slab], 1u);
+        }
+      }
+      continue;
+    }
+    // quantise item: the slab maximum is final once all T absmax items of the slab have reported
+    if (threadIdx.x == 0) {
+      while (*((volatile unsigned*)&done[slab]) < (unsigned)T) __nanosleep(64);
+      __threadfence();
+      s_warp_max[0] = __uint_as_float(*((volatile unsigned*)&amax[slab]));
+    }
+    __syncthreads();
+    const float sc = fmaxf(s_warp_max[0] / 127.0f, 1e-8f);  // fa_tc_int8_b.cu:104
+    const float inv = 1.0f / sc;                             // fa_tc_int8_b.cu:106
+    if (t == 0 && threadIdx.x == 0) scales[slab] = sc;
+    if (z < 2) {
+      int8_t* dst = z == 0 ? Qp : Kp;
+#pragma unroll
+      for (int k = 0; k < kLoads; ++k) {
+        const int n = n0 + rsub + k * kRowsPerIter;
+        const int q0 = quant1(x[k].x, inv), q1 = quant1(x[k].y, inv);
+        const int q2 = quant1(x[k].z, inv), q3 = quant1(x[k].w, inv);
+        const uint32_t pk = (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) |
+                            ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+        *reinterpret_cast<uint32_t*>(dst + ((size_t)unit * n_pad + n) * kD + vec * 4) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kLoads; ++k) {
+        const int r = rsub + k * kRowsPerIter;
+        tile[r * kStride + vec * 4 + 0] = __float2half_rn((float)quant1(x[k].x, inv));
+        tile[r * kStride + vec * 4 + 1] = __float2half_rn((float)quant1(x[k].y, inv));
+        tile[r * kStride + vec * 4 + 2] = __float2half_rn((float)quant1(x[k].z, inv));
+        tile[r * kStride + vec * 4 + 3] = __float2half_rn((float)quant1(x[k].w, inv));
+      }
+      __syncthreads();
+      constexpr int kPairs = kStreamRows / 2;   // threads per d-row: each emits 2 consecutive keys
+      const int kp = threadIdx.x % kPairs;
+      for (int dd = threadIdx.x / kPairs; dd < kD; dd += kStreamThreads / kPairs) {
+        __half2 o2 = __halves2half2(tile[(2 * kp) * kStride + dd], tile[(2 * kp + 1) * kStride + dd]);
+        *reinterpret_cast<__half2*>(Vt + ((size_t)unit * kD + dd) * n_pad + n0 + 2 * kp) = o2;
+      }
+    }
+  }
+}
+
+template <int kD, typename TIn>
+cudaError_t launch_stream_cfg(const PrepareArgs& a, unsigned* ctl) {
+  const int units = a.B * a.H;
+  // ctl layout: [0] queue head, [16 .. 16 + 3u) slab maxima, [16 + 3u .. 16 + 6u) tile counters
+  cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(unsigned) * (16 + 6 * (size_t)units), a.stream);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  stream_quantize_kernel<kD, TIn><<<2 * sms, kStreamThreads, 0, a.stream>>>(
+      reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), a.scales,
+      reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp), reinterpret_cast<__half*>(a.Vt), ctl, ctl + 16,
+      ctl + 16 + 3 * (size_t)units, a.N, a.H, a.d, a.n_pad, units, a.rope);
+  return cudaGetLastError();
+}
+
+template <int kD, typename TIn>
 cudaError_t launch_fused_cfg(const PrepareArgs& a) {
-  auto kern = fused_quantize_kernel<kD>;
+  auto kern = fused_quantize_kernel<kD, TIn>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes);
   if (e != cudaSuccess) return e;
   dim3 grid(kClusterSize, a.B * a.H, 3);
   kern<<<grid, kFusedThreads, kFusedSmemBytes, a.stream>>>(
-      a.Q, a.K, a.V, a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
+      reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
       reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
   return cudaGetLastError();
 }
 
-template <bool kInt8, int kD>
+template <int kOut, int kD, typename TIn>
 cudaError_t launch_prepare_cfg(const PrepareArgs& a) {
   dim3 grid(a.n_pad / kPrepRows, a.B * a.H, 3);
-  prepare_kernel<kInt8, kD><<<grid, kPrepThreads, 0, a.stream>>>(
-      a.Q, a.K, a.V, a.scales, a.Qp, a.Kp, reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad,
-      a.rope);
+  prepare_kernel<kOut, kD, TIn><<<grid, kPrepThreads, 0, a.stream>>>(
+      reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V),
+      a.scales, a.Qp, a.Kp, reinterpret_cast<uint16_t*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
   return cudaGetLastError();
 }
+
+// in_dtype (0 fp32, 1 fp16, 2 bf16) -> element type
+#define QMHA_BY_DTYPE(a, CALL)                                    \
+  switch ((a).in_dtype) {                                         \
+    case 0: { using TIn = float; return CALL; }                   \
+    case 1: { using TIn = __half; return CALL; }                  \
+    case 2: { using TIn = __nv_bfloat16; return CALL; }           \
+  }                                                               \
+  return cudaErrorInvalidValue;
+template <int kD> cudaError_t launch_fused_d(const PrepareArgs& a) { QMHA_BY_DTYPE(a, (launch_fused_cfg<kD, TIn>(a))) }
+template <int kD> cudaError_t launch_stream_d(const PrepareArgs& a, unsigned* ctl) { QMHA_BY_DTYPE(a, (launch_stream_cfg<kD, TIn>(a, ctl))) }
+template <int kD> cudaError_t launch_block_d(const PrepareArgs& a) { QMHA_BY_DTYPE(a, (launch_block_cfg<kD, TIn>(a))) }
+template <int kOut, int kD> cudaError_t launch_prepare_d(const PrepareArgs& a) { QMHA_BY_DTYPE(a, (launch_prepare_cfg<kOut, kD, TIn>(a))) }
+template <typename TIn>
+cudaError_t launch_absmax_t(const PrepareArgs& a, unsigned* amax_bits) {
+  dim3 grid((a.N + kAbsmaxRows - 1) / kAbsmaxRows, a.B, 3);
+  absmax_kernel<TIn><<<grid, kAbsmaxThreads, sizeof(unsigned) * a.H, a.stream>>>(
+      reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), amax_bits,
+      a.N, a.H, a.d, a.d_pad, a.rope);
+  return cudaGetLastError();
+}
+cudaError_t launch_absmax_d(const PrepareArgs& a, unsigned* amax_bits) { QMHA_BY_DTYPE(a, (launch_absmax_t<TIn>(a, amax_bits))) }
 
 }  // namespace
 
@@ -626,10 +849,7 @@ cudaError_t launch_absmax_and_scales(const PrepareArgs& a, unsigned* amax_bits, 
   const int units = a.B * a.H;
   cudaError_t e = cudaMemsetAsync(amax_bits, 0, sizeof(unsigned) * 3 * units, a.stream);
   if (e != cudaSuccess) return e;
-  dim3 grid((a.N + kAbsmaxRows - 1) / kAbsmaxRows, a.B, 3);
-  absmax_kernel<<<grid, kAbsmaxThreads, sizeof(unsigned) * a.H, a.stream>>>(a.Q, a.K, a.V, amax_bits,
-                                                                           a.N, a.H, a.d);
-  e = cudaGetLastError();
+  e = launch_absmax_d(a, amax_bits);
   if (e != cudaSuccess) return e;
   finalize_scales_kernel<<<3, 256, 0, a.stream>>>(amax_bits, a.scales, units, per_tensor);
   return cudaGetLastError();
@@ -638,9 +858,20 @@ cudaError_t launch_absmax_and_scales(const PrepareArgs& a, unsigned* amax_bits, 
 // Single-pass INT8 preparation with per-(batch, head) scales (requires d % 4 == 0).
 cudaError_t launch_fused_quantize(const PrepareArgs& a) {
   switch (a.d_pad) {
-    case 32: return launch_fused_cfg<32>(a);
-    case 64: return launch_fused_cfg<64>(a);
-    case 128: return launch_fused_cfg<128>(a);
+    case 32: return launch_fused_d<32>(a);
+    case 64: return launch_fused_d<64>(a);
+    case 128: return launch_fused_d<128>(a);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// Single-launch INT8 preparation with per-(batch, head) scales on a persistent grid (requires d % 4 == 0);
+// ctl = 16 + 6 * B * H unsigned words of scratch.
+cudaError_t launch_stream_quantize(const PrepareArgs& a, unsigned* ctl) {
+  switch (a.d_pad) {
+    case 32: return launch_stream_d<32>(a, ctl);
+    case 64: return launch_stream_d<64>(a, ctl);
+    case 128: return launch_stream_d<128>(a, ctl);
   }
   return cudaErrorInvalidValue;
 }
@@ -648,9 +879,9 @@ cudaError_t launch_fused_quantize(const PrepareArgs& a) {
 // Single-pass INT8 preparation with per-(batch, head, 32-row block) scales (requires d % 4 == 0).
 cudaError_t launch_block_quantize(const PrepareArgs& a) {
   switch (a.d_pad) {
-    case 32: return launch_block_cfg<32>(a);
-    case 64: return launch_block_cfg<64>(a);
-    case 128: return launch_block_cfg<128>(a);
+    case 32: return launch_block_d<32>(a);
+    case 64: return launch_block_d<64>(a);
+    case 128: return launch_block_d<128>(a);
   }
   return cudaErrorInvalidValue;
 }
@@ -664,15 +895,21 @@ cudaError_t launch_block_aux(const float* scales_v, float* aux, float* vmax, int
 cudaError_t launch_prepare(const PrepareArgs& a) {
   if (a.int8) {
     switch (a.d_pad) {
-      case 32: return launch_prepare_cfg<true, 32>(a);
-      case 64: return launch_prepare_cfg<true, 64>(a);
-      case 128: return launch_prepare_cfg<true, 128>(a);
+      case 32: return launch_prepare_d<0, 32>(a);
+      case 64: return launch_prepare_d<0, 64>(a);
+      case 128: return launch_prepare_d<0, 128>(a);
+    }
+  } else if (a.bf16) {
+    switch (a.d_pad) {
+      case 32: return launch_prepare_d<2, 32>(a);
+      case 64: return launch_prepare_d<2, 64>(a);
+      case 128: return launch_prepare_d<2, 128>(a);
     }
   } else {
     switch (a.d_pad) {
-      case 32: return launch_prepare_cfg<false, 32>(a);
-      case 64: return launch_prepare_cfg<false, 64>(a);
-      case 128: return launch_prepare_cfg<false, 128>(a);
+      case 32: return launch_prepare_d<1, 32>(a);
+      case 64: return launch_prepare_d<1, 64>(a);
+      case 128: return launch_prepare_d<1, 128>(a);
     }
   }
   return cudaErrorInvalidValue;

@@ -6,15 +6,17 @@
 namespace qmha {
 
 struct PrepareArgs {
-  const float* Q;  // [B, N, H*d] fp32, device
-  const float* K;
-  const float* V;
+  const void* Q;   // [B, N, H*d] of in_dtype, device
+  const void* K;
+  const void* V;
+  int in_dtype = 0;  // 0 = fp32 (the reference's API), 1 = fp16, 2 = bf16
   float* scales;   // [3, B*H] (INT8) — written by launch_absmax_and_scales, read by launch_prepare
   void* Qp;        // [B*H, n_pad, d_pad] int8 / fp16
   void* Kp;
   void* Vt;        // [B*H, d_pad, n_pad] fp16
   int B, N, H, d, n_pad, d_pad;
   bool int8;
+  bool bf16 = false;  // 16-bit kernels: operands converted to bf16 instead of fp16
   cudaStream_t stream;
   // fused RoPE (utils/verify.cu:9-23 applied to Q and K rows before absmax / quantisation):
   // table of {cos, sin}(pos * base^(-2k/d)) as float2 [N][d/2], built on the host; nullptr = off
@@ -25,6 +27,8 @@ struct PrepareArgs {
 cudaError_t launch_absmax_and_scales(const PrepareArgs& a, unsigned* amax_bits, int per_tensor);
 // absmax + quantise + re-layout in ONE launch (cluster kernel; INT8, per-(batch,head) scales, d%4==0).
 cudaError_t launch_fused_quantize(const PrepareArgs& a);
+// the same on a persistent grid without clusters (default for per-head scales); ctl: 16 + 6*B*H words of scratch
+cudaError_t launch_stream_quantize(const PrepareArgs& a, unsigned* ctl);
 // single-pass quantise with the reference's per-32-row-block scales; scales = [3][B*H][n_pad/32]
 cudaError_t launch_block_quantize(const PrepareArgs& a);
 // per unit max V scale + per block {log2 r, 1/r}, r = sV_block / sV_max (attention, block mode)

@@ -251,6 +251,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// two fp32 -> packed bf16x2 (lo = first argument)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // packed exp2 on two fp16 values (one MUFU.EX2.F16 op)
 __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
   uint32_t y;

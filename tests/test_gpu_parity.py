@@ -397,9 +397,9 @@ def test_fused_rope_matches_the_cpu_reference_with_rope(qm, torch, oracle, shape
             assert np.array_equal(sch[i].cpu().numpy(), s), "QK"[i]
         outh = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_HEAD)
         assert _err(outh.cpu().numpy(), ref)[0] <= INT8_MAX_ABS
-        # unsupported combination fails loudly instead of silently skipping the rotation
-        with pytest.raises(qm.QmhaError):
-            qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_TENSOR)
+        # per-tensor scales (two-pass path) rotate as well: tests/test_gpu_api.py::test_fused_rope_with_per_tensor_scales
+        outt = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_TENSOR)
+        assert _err(outt.cpu().numpy(), ref)[0] <= INT8_MAX_ABS
     finally:
         qm.set_rope(False)
     again = qm.forward(tq, tk, tv, h, kernel="int8", gran=qm.GRAN_BLOCK)
