@@ -354,8 +354,8 @@ int prepare_impl(Workspace* w, const void* Q, const void* K, const void* V, int 
     // scales need a global maximum first and keep the two-pass path (as does an odd head dim).
     static const bool two_pass_env = getenv("QMHA_TWO_PASS_QUANT") != nullptr;
     if (gran == QMHA_GRAN_HEAD && (d & 3) == 0 && !two_pass_env) {
-      static const bool cluster_env = getenv("QMHA_CLUSTER_QUANT") != nullptr;   // the older cluster kernel, for A/B
-      if (cluster_env) {
+      // cluster kernel by default; QMHA_STREAM_QUANT=1: the persistent-grid variant (same results, same speed)
+      if (getenv("QMHA_STREAM_QUANT") == nullptr) {
         if ((e = qmha::launch_fused_quantize(a)) != cudaSuccess) return fail_cuda("fused quantise launch", e);
       } else {
         if ((e = qmha::launch_stream_quantize(a, amax)) != cudaSuccess) return fail_cuda("stream quantise launch", e);

@@ -657,27 +657,40 @@ fused_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
 }
 
 // ------------------------------------------------------------------------------------------------
-// stream_quantize_kernel: per-(batch, head) scales in ONE launch without clusters.  The cluster kernel above keeps
-// only ~15 slabs in flight and alternates between an HBM phase and an L2 phase per cluster (1.24 ms at the headline
-// shape = 53 % of the HBM roofline).  Here a persistent grid pulls items off one queue ordered as
-//     round r:  absmax of the T 128-row tiles of slab r,  then  quantise + re-layout of the tiles of slab r - kLag
+// stream_quantize_kernel: per-(batch, head) scales in ONE launch without clusters (QMHA_STREAM_QUANT=1 selects it;
+// the cluster kernel above stays the default).  The cluster kernel keeps only ~15 slabs in flight and alternates
+// between an HBM phase and an L2 phase per cluster (1.17-1.24 ms at the headline shape = 53-56 % of the HBM roofline).
+// Here a persistent grid pulls items off one queue ordered as
+//     round r:  absmax of the T row tiles of slab r,  then  quantise + re-layout of the tiles of slab r - kLag
 // so HBM reads (absmax items), L2 re-reads and HBM writes (quantise items) of different slabs overlap all the time,
-// and the re-read of a slab follows its first read by ~kLag slabs of traffic (a few MB: L2 hits).
+// and the re-read of a slab follows its first read by ~kLag slabs of traffic (a few MB: L2 hits — ncu: 3.22 GB of
+// DRAM reads = one read of the inputs).  Measured at the headline shape, same box (tools/quant_ab.py): 512 threads x
+// 2 CTAs/SM, 128-row items 1.34 ms; 64-row items 1.96 ms; 256 threads x 4 CTAs/SM, 64-row items, lag 3 (default)
+// 1.175 ms; x 6 CTAs/SM 1.24 ms; cluster kernel 1.165 ms; block kernel (one pass, no second read) 0.63 ms.  I.e. the
+// second read is not an HBM problem any more (DRAM runs at 3.2 TB/s) but both variants sit at ~55 % of the HBM
+// roofline: the per-item serialisation (queue fetch, load, reduce, store) leaves too few bytes in flight per SM.
 // A quantise item waits for the tile counter of its slab; every absmax item of that slab was taken off the queue
 // earlier by a CTA that is running, so the wait always ends.
 //   ctl[0] = queue head;  amax[s], done[s] per slab s = z * units + unit (zeroed by the launcher)
 #ifndef QMHA_STREAM_ROWS
-#define QMHA_STREAM_ROWS 128
+#define QMHA_STREAM_ROWS 64
 #endif
 #ifndef QMHA_STREAM_LAG
-#define QMHA_STREAM_LAG 2
+#define QMHA_STREAM_LAG 3
 #endif
-constexpr int kStreamThreads = 512;
+#ifndef QMHA_STREAM_THREADS
+#define QMHA_STREAM_THREADS 256
+#endif
+#ifndef QMHA_STREAM_CTAS
+#define QMHA_STREAM_CTAS 4
+#endif
+constexpr int kStreamThreads = QMHA_STREAM_THREADS;
+constexpr int kStreamCtas = QMHA_STREAM_CTAS;
 constexpr int kStreamRows = QMHA_STREAM_ROWS;
 constexpr int kStreamLag = QMHA_STREAM_LAG;
 
 template <int kD, typename TIn>
-__global__ void __launch_bounds__(kStreamThreads, 2)
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtas)
 stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, const TIn* __restrict__ V,
                        float* __restrict__ scales, int8_t* __restrict__ Qp, int8_t* __restrict__ Kp,
                        __half* __restrict__ Vt, unsigned* __restrict__ ctl, unsigned* __restrict__ amax,
@@ -793,7 +806,7 @@ cudaError_t launch_stream_cfg(const PrepareArgs& a, unsigned* ctl) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  stream_quantize_kernel<kD, TIn><<<2 * sms, kStreamThreads, 0, a.stream>>>(
+  stream_quantize_kernel<kD, TIn><<<kStreamCtas * sms, kStreamThreads, 0, a.stream>>>(
       reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), a.scales,
       reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp), reinterpret_cast<__half*>(a.Vt), ctl, ctl + 16,
       ctl + 16 + 3 * (size_t)units, a.N, a.H, a.d, a.n_pad, units, a.rope);

@@ -343,3 +343,34 @@ def test_profile_binary_flags_exit_codes_and_cache_files(torch, oracle, reflib, 
     r = subprocess.run([exe, "-k", kernel, f"--N={N}", f"--d_model={dm}", f"--h={h}", "--B=2", "--runs=1", "--rope", "--json"],
                        cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ---------------------------------------------------------------------------------- per-head quantiser variants
+@pytest.mark.parametrize("shape", [(1, 50, 64, 8), (2, 300, 256, 2), (1, 1024, 512, 4), (3, 129, 96, 3), (2, 4096, 256, 2)])
+def test_persistent_per_head_quantiser_is_bit_identical(qm, torch, oracle, shape, monkeypatch):
+    """QMHA_STREAM_QUANT=1 selects the persistent-grid per-head quantiser (queue of absmax / quantise items, no
+    clusters): codes, scales and padding identical to the cluster kernel and to the CPU restatement, with and
+    without fused RoPE, for fp32 and 16-bit inputs."""
+    B, N, dm, h = shape
+    d = dm // h
+    q, k, v = (np.stack(x) for x in zip(*[oracle.golden_inputs(N, dm, h, rope=False) for _ in range(B)]))
+    q[1:] *= 1.7
+    tq, tk, tv = _dev(torch, q, k, v)
+    for rope in ((False, True) if d % 8 == 0 else (False,)):
+        monkeypatch.delenv("QMHA_STREAM_QUANT", raising=False)
+        ref = qm.quantize_qkv(tq, tk, tv, h, qm.GRAN_HEAD, rope=rope)
+        monkeypatch.setenv("QMHA_STREAM_QUANT", "1")
+        got = qm.quantize_qkv(tq, tk, tv, h, qm.GRAN_HEAD, rope=rope)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(ref, got)), rope
+        got16 = qm.quantize_qkv(tq.half(), tk.half(), tv.half(), h, qm.GRAN_HEAD, rope=rope)
+        monkeypatch.delenv("QMHA_STREAM_QUANT", raising=False)
+        ref16 = qm.quantize_qkv(tq.half(), tk.half(), tv.half(), h, qm.GRAN_HEAD, rope=rope)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(ref16, got16)), rope
+    codes, s = oracle.quantize(k, h, "head")
+    monkeypatch.setenv("QMHA_STREAM_QUANT", "1")
+    Qp, Kp, Vt, sc = qm.quantize_qkv(tq, tk, tv, h, qm.GRAN_HEAD, rope=False)
+    monkeypatch.delenv("QMHA_STREAM_QUANT", raising=False)
+    assert np.array_equal(_unpack_rows(Kp, B, N, h, d), codes) and np.array_equal(sc[1].cpu().numpy(), s)
+    assert (Qp[:, N:, :] == 0).all() and (Vt[:, :, N:] == 0).all()

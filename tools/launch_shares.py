@@ -7,7 +7,7 @@ tot = collections.Counter(); cnt = collections.Counter()
 for r in rows[1:]:
     if len(r) <= ix["Metric Value"] or r[ix["Metric Name"]] != "gpu__time_duration.sum": continue
     name = r[ix["Kernel Name"]]
-    m = re.search(r"(attn_fwd_kernel|block_quantize_kernel|block_aux_kernel|fused_quantize_kernel|prepare_kernel|absmax_kernel|finalize_scales_kernel)", name)
+    m = re.search(r"(attn_fwd_kernel|block_quantize_kernel|block_aux_kernel|fused_quantize_kernel|stream_quantize_kernel|prepare_kernel|absmax_kernel|finalize_scales_kernel)", name)
     key = m.group(1) if m else "torch/other"
     v = float(r[ix["Metric Value"]].replace(",", ""))
     unit = r[ix["Metric Unit"]]

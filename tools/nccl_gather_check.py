@@ -1,0 +1,40 @@
+"""Multi-GPU check under torchrun (NCCL): every rank computes ITS (batch x head) slabs of one problem through the
+C-ABI, sharding.gather_outputs() replicates the result over NVLink (one all-gather, caller-side, never on the hot
+path), and every rank compares the replicated tensor with a full single-GPU forward — bit-identical, because the
+scales are per head or finer.  usage: python -m torch.distributed.run --nproc-per-node N tools/nccl_gather_check.py"""
+import os, sys
+import torch
+import torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import quantizedmha_b200 as qm
+from quantizedmha_b200.sharding import shard_slabs, slab_view, gather_outputs
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+B, H, N, d = 3, 5, 1000, 64          # 15 units: uneven split for every world size > 1
+gen = torch.Generator(device=dev).manual_seed(1234)      # same inputs on every rank
+q, k, v = (torch.rand((B, N, H * d), device=dev, generator=gen) for _ in range(3))
+ok = True
+for kernel, gran in (("int8", qm.GRAN_BLOCK), ("int8", qm.GRAN_HEAD), ("f16", qm.GRAN_HEAD)):
+    out = torch.zeros_like(q)
+    for (b, h0, h1) in shard_slabs(B, H, world, rank):
+        sl = [slab_view(t, b, h0, h1, H).contiguous() for t in (q, k, v)]
+        slab_view(out, b, h0, h1, H).copy_(qm.forward(*sl, h1 - h0, kernel=kernel, gran=gran))
+    torch.cuda.synchronize()
+    qm.binding.check_async_error()
+    gather_outputs(out, B, H)
+    full = qm.forward(q, k, v, H, kernel=kernel, gran=gran)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(out, full))
+    ok = ok and same
+    if rank == 0:
+        print(f"{kernel} gran={gran}: gathered == single-GPU forward: {same}", flush=True)
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("NCCL gather check", "OK" if int(flag.item()) == 1 else "FAILED", f"({world} ranks)", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)

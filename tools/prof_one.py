@@ -1,5 +1,5 @@
 """Runs the quantise + attention kernels a few times on the C4 shape (for ncu captures).
-usage: prof_one.py [int8|f16] [B,H,N,d] [reps] [block|head]"""
+usage: prof_one.py [int8|f16|bf16] [B,H,N,d] [reps] [block|head]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,7 +17,7 @@ out = torch.empty_like(tq)
 if kern == "int8":
     Qp, Kp, Vt, sc = qm.quantize_qkv(tq, tk, tv, H, gran)
 else:
-    Qp, Kp, Vt = qm.convert_qkv_f16(tq, tk, tv, H); sc = None
+    Qp, Kp, Vt = qm.convert_qkv_f16(tq, tk, tv, H, kernel=kern); sc = None
 for _ in range(reps):
     qm.attention_prepared(Qp, Kp, Vt, sc, B, N, dm, H, kern, out=out, gran=gran)
 torch.cuda.synchronize()

@@ -21,13 +21,16 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 
 enum Pat {
   kI8ss64 = 0, kI8ss64acc, kI8ss128, kI8ss256, kF16ts128, kPvQk, kPvQk2tiles, kI8ts64, kI8ts128, kF16ss64x8,
-  kF16ss128x8, kI8ss64x2tiles, kPvQk128, kF16ts128x8, kI8ss64one, kF16ts256, kNumPat
+  kF16ss128x8, kI8ss64x2tiles, kPvQk128, kF16ts128x8, kI8ss64one, kF16ts256, kCrossSeq, kCrossIl, kF16CrossSeq, kF16CrossIl, kF16SameSeq, kNumPat
 };
 static const char* kNames[kNumPat] = {
     "i8 SS N64 x4 (K=128)", "i8 SS N64 x4 acc=1", "i8 SS N128 x4", "i8 SS N256 x4", "f16 TS N128 K16 x4 (P.V 64 keys)",
     "PV(f16 TS N128 x4) + QK(i8 SS N64 x4)", "same, tile0 + tile1 interleaved per op", "i8 TS N64 x4", "i8 TS N128 x4",
     "f16 SS N64 K16 x8", "f16 SS N128 K16 x8", "i8 SS N64 x4, tile0 then tile1", "PV(f16 TS N128 x8) + QK(i8 SS N128 x4)",
-    "f16 TS N128 K16 x8 (P.V 128 keys)", "i8 SS N64 x1", "f16 TS N256 K16 x4"};
+    "f16 TS N128 K16 x8 (P.V 128 keys)", "i8 SS N64 x1", "f16 TS N256 K16 x4",
+    "INT8 kernel: PV(t0) x4 then QK(t1) x4", "INT8 kernel: PV(t0) / QK(t1) interleaved 1:1",
+    "FP16 kernel: PV(t0) x4 then QK(t1) f16 SS N64 x8", "FP16 kernel: PV(t0) / QK(t1) interleaved 1:2",
+    "FP16 kernel: PV(t0) x4 then QK(t0) f16 SS N64 x8"};
 
 // TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); Q in TMEM (TS int8): columns 192.. (overlaps S1, timing only)
 template <int PAT>
@@ -71,6 +74,28 @@ __device__ __forceinline__ void pattern(uint32_t tb, const uint64_t (&qa)[2][8],
   if constexpr (PAT == kPvQk) { pv64(0); qk64(0, false); }
   if constexpr (PAT == kPvQk2tiles) { pv64(0); qk64(0, false); pv64(1); qk64(1, false); }
   if constexpr (PAT == kI8ss64x2tiles) { qk64(0, false); qk64(1, false); }
+  if constexpr (PAT == kCrossSeq) { pv64(0); qk64(1, false); }
+  if constexpr (PAT == kCrossIl) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      mma_f16_ts(tb + 256, tb + (64 - sbuf) + ks * 8, vb[ks], f16_128, 1u);
+      mma_i8_ss(tb + 128 + sbuf, qa[1][ks], kb[ks], i8_64, ks > 0);
+    }
+  }
+  if constexpr (PAT == kF16CrossSeq || PAT == kF16SameSeq) {
+    pv64(0);
+    constexpr int t = PAT == kF16CrossSeq ? 1 : 0;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) mma_f16_ss(tb + t * 128 + sbuf, qa[t][ks], kb[ks], f16_64, ks > 0);
+  }
+  if constexpr (PAT == kF16CrossIl) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      mma_f16_ts(tb + 256, tb + (64 - sbuf) + ks * 8, vb[ks], f16_128, 1u);
+      mma_f16_ss(tb + 128 + sbuf, qa[1][2 * ks], kb[2 * ks], f16_64, ks > 0);
+      mma_f16_ss(tb + 128 + sbuf, qa[1][2 * ks + 1], kb[2 * ks + 1], f16_64, 1u);
+    }
+  }
   if constexpr (PAT == kI8ts64) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) mma_i8_ts(tb + sbuf, tb + 192 + ks * 8, kb[ks], i8_64, ks > 0);
@@ -170,7 +195,7 @@ __global__ void __launch_bounds__(192, 1) k(int reps, int issuers, int traffic, 
 template <int PAT>
 void run(long long* cyc) {
   cudaFuncSetAttribute(k<PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024 + 1024);
-  constexpr bool two_ok = PAT != kPvQk2tiles && PAT != kI8ss64x2tiles && PAT != kI8ss256 && PAT != kF16ts256;
+  constexpr bool two_ok = PAT != kPvQk2tiles && PAT != kI8ss64x2tiles && PAT != kI8ss256 && PAT != kF16ts256 && PAT < kCrossSeq;
   for (int issuers : {1, 2}) {
     if (issuers == 2 && !two_ok) continue;
     for (int traffic : {0, 1}) {
@@ -194,5 +219,6 @@ int main() {
   run<kI8ts64>(cyc); run<kI8ts128>(cyc);
   run<kF16ts128>(cyc); run<kF16ts128x8>(cyc); run<kF16ts256>(cyc); run<kF16ss64x8>(cyc); run<kF16ss128x8>(cyc);
   run<kI8ss64x2tiles>(cyc); run<kPvQk>(cyc); run<kPvQk2tiles>(cyc); run<kPvQk128>(cyc);
+  run<kCrossSeq>(cyc); run<kCrossIl>(cyc); run<kF16SameSeq>(cyc); run<kF16CrossSeq>(cyc); run<kF16CrossIl>(cyc);
   return 0;
 }
