@@ -666,9 +666,13 @@ fused_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
 // and the re-read of a slab follows its first read by ~kLag slabs of traffic (a few MB: L2 hits — ncu: 3.22 GB of
 // DRAM reads = one read of the inputs).  Measured at the headline shape, same box (tools/quant_ab.py): 512 threads x
 // 2 CTAs/SM, 128-row items 1.34 ms; 64-row items 1.96 ms; 256 threads x 4 CTAs/SM, 64-row items, lag 3 (default)
-// 1.175 ms; x 6 CTAs/SM 1.24 ms; cluster kernel 1.165 ms; block kernel (one pass, no second read) 0.63 ms.  I.e. the
-// second read is not an HBM problem any more (DRAM runs at 3.2 TB/s) but both variants sit at ~55 % of the HBM
-// roofline: the per-item serialisation (queue fetch, load, reduce, store) leaves too few bytes in flight per SM.
+// 1.175 ms; x 6 CTAs/SM 1.24 ms; x 3 CTAs/SM 1.42 ms; cluster kernel 1.165 ms; block kernel (one pass, no second
+// read) 0.63 ms.  Prefetching the queue index one item ahead and decoding items / computing the scale in one thread
+// (ncu: the per-thread divisions were a quarter of the instructions, barrier stalls 39 %) changed nothing (1.19-1.21 ms).
+// I.e. the second read is not an HBM problem any more (DRAM runs at 3.6 TB/s), yet every implementation of this
+// granularity lands on the same ~1.17 ms: 24*E bytes of loads = 5.5 TB/s into the SMs, which is also what the block
+// kernel's 12*E in 0.63 ms and the two-pass path's 24*E in 1.3 ms amount to — the load path into the SMs (half of the
+// L2 hits cross the die boundary), not HBM, is the common limit, and a per-head scale needs every element twice.
 // A quantise item waits for the tile counter of its slab; every absmax item of that slab was taken off the queue
 // earlier by a CTA that is running, so the wait always ends.
 //   ctl[0] = queue head;  amax[s], done[s] per slab s = z * units + unit (zeroed by the launcher)
@@ -702,7 +706,7 @@ stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, con
   constexpr int kStride = kD + 2;
   __shared__ __half tile[kStreamRows * kStride];
   __shared__ float s_warp_max[kStreamThreads / 32];
-  __shared__ unsigned s_item;
+  __shared__ int s_dec[2][6];
   const int T = n_pad / kStreamRows;
   const int slabs = 3 * units;
   const unsigned total = (unsigned)(slabs + kStreamLag) * 2u * (unsigned)T;
@@ -710,19 +714,28 @@ stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, con
   const int rsub = threadIdx.x / kVecPerRow;
   const bool col_ok = vec * 4 < d;
   const int d_model = H * d;
-  for (;;) {
-    __syncthreads();   // s_item / tile / s_warp_max of the previous item are no longer read
-    if (threadIdx.x == 0) s_item = atomicAdd(&ctl[0], 1u);
-    __syncthreads();
-    const unsigned item = s_item;
-    if (item >= total) break;
+  // Item decode (four divisions by run-time values) and the scale arithmetic are done by ONE thread and broadcast
+  // through shared memory: done per thread they were a quarter of the kernel's instructions (ncu).
+  auto decode = [&](unsigned item, int* o) {   // o = {slab (-1: nothing to do), tile, quantise?, z, b, head}
+    o[0] = -1;
+    if (item >= total) { o[0] = -2; return; }
     const int round = (int)(item / (2u * T)), j = (int)(item % (2u * T));
-    const bool quant = j >= T;
+    const int quant = j >= T;
     const int slab = quant ? round - kStreamLag : round;
-    if (slab < 0 || slab >= slabs) continue;
-    const int t = quant ? j - T : j;
-    const int z = slab / units, unit = slab % units;
-    const int b = unit / H, head = unit % H;
+    if (slab < 0 || slab >= slabs) return;
+    const int unit = slab % units;
+    o[0] = slab; o[1] = quant ? j - T : j; o[2] = quant; o[3] = slab / units; o[4] = unit / H; o[5] = unit % H;
+  };
+  if (threadIdx.x == 0) decode(atomicAdd(&ctl[0], 1u), s_dec[0]);
+  __syncthreads();
+  for (int par = 0;; par ^= 1) {
+    const int slab = s_dec[par][0];
+    if (slab == -2) break;
+    if (slab >= 0) {
+    const int t = s_dec[par][1];
+    const bool quant = s_dec[par][2] != 0;
+    const int z = s_dec[par][3], b = s_dec[par][4], head = s_dec[par][5];
+    const int unit = slab - z * units;
     const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
     const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
     const int n0 = t * kStreamRows;
@@ -736,6 +749,8 @@ stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, con
 #pragma unroll
       for (int k = 0; k < kLoads; ++k) x[k] = rope_rotate(x[k], vec, n0 + rsub + k * kRowsPerIter, N, d, rope);
     }
+    // next item: the queue round trip (~1 us) and the decode hide behind this item's loads
+    if (threadIdx.x == 0) decode(atomicAdd(&ctl[0], 1u), s_dec[par ^ 1]);
     if (!quant) {
       float m = 0.f;
 #pragma unroll
@@ -754,18 +769,18 @@ stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, con
           atomicAdd(&done[slab], 1u);
         }
       }
-      continue;
-    }
+    } else {
     // quantise item: the slab maximum is final once all T absmax items of the slab have reported
     if (threadIdx.x == 0) {
       while (*((volatile unsigned*)&done[slab]) < (unsigned)T) __nanosleep(64);
       __threadfence();
-      s_warp_max[0] = __uint_as_float(*((volatile unsigned*)&amax[slab]));
+      const float sc1 = fmaxf(__uint_as_float(*((volatile unsigned*)&amax[slab])) / 127.0f, 1e-8f);  // fa_tc_int8_b.cu:104
+      s_warp_max[0] = sc1;
+      s_warp_max[1] = 1.0f / sc1;                             // fa_tc_int8_b.cu:106
+      if (t == 0) scales[slab] = sc1;
     }
     __syncthreads();
-    const float sc = fmaxf(s_warp_max[0] / 127.0f, 1e-8f);  // fa_tc_int8_b.cu:104
-    const float inv = 1.0f / sc;                             // fa_tc_int8_b.cu:106
-    if (t == 0 && threadIdx.x == 0) scales[slab] = sc;
+    const float inv = s_warp_max[1];
     if (z < 2) {
       int8_t* dst = z == 0 ? Qp : Kp;
 #pragma unroll
@@ -794,6 +809,11 @@ stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, con
         *reinterpret_cast<__half2*>(Vt + ((size_t)unit * kD + dd) * n_pad + n0 + 2 * kp) = o2;
       }
     }
+    }   // quantise item
+    } else {   // nothing to do for this queue slot (first / last kStreamLag rounds): just fetch the next one
+      if (threadIdx.x == 0) decode(atomicAdd(&ctl[0], 1u), s_dec[par ^ 1]);
+    }
+    __syncthreads();   // item done: the next item is visible; tile / s_warp_max may be reused
   }
 }
 
