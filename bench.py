@@ -389,6 +389,24 @@ def run_native(args):
         raise SystemExit(f"bench.py: the host-buffer path and the device path disagree (max abs {e2e_maxdiff})")
     barrier()
     roof_ms = copy_roof_ms(torch, dev, [hq, hk, hv], ho) * (Bl / Be)
+    # the same call for a 16-bit caller (qmha_forward_host_ex, fp16 host buffers in and out): half the PCIe bytes
+    e2e16 = None
+    if not args.no_e2e16:
+        h16 = [t.to(torch.float16).pin_memory() for t in (hq, hk, hv)]
+        ho16 = torch.empty((Be, N, dm), dtype=torch.float16, pin_memory=True)
+        call16 = lambda: job.chk(L.qmha_forward_host_ex(h16[0].data_ptr(), h16[1].data_ptr(), h16[2].data_ptr(), ho16.data_ptr(),
+                                                        Be, N, dm, H, job.kid, gran_e2e, 1, 1))
+        call16()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call16()
+        e2e16_ms = (time.perf_counter() - t0) / e2e_steps * 1e3 * (Bl / Be)
+        diff16 = float((ho16.to(dev).float() - job.out[:Be]).abs().max().item())   # vs the fp32-input device result
+        (e2e16_ms,) = max_over_ranks([e2e16_ms])
+        e2e16 = {"ms_per_step": e2e16_ms, "h2d_bytes_per_step": 3 * Bl * N * dm * 2, "d2h_bytes_per_step": Bl * N * dm * 2,
+                 "api": "qmha_forward_host_ex, fp16 pinned host buffers in and out", "max_abs_vs_fp32_path": diff16}
+        del h16, ho16
     del hq, hk, hv, ho
 
     ms_step, attn_ms, prep_ms, e2e_ms, roof_ms = max_over_ranks([ms_step, attn_ms, prep_ms, e2e_ms, roof_ms])
@@ -505,7 +523,8 @@ def run_native(args):
                 "api": "qmha_forward_host (pinned host buffers; copies pipelined per batch entry x head group)",
                 "host_placement": numa, "copy_roof_ms": roof_ms, "frac_of_copy_roof": roof_ms / e2e_ms,
                 "copy_roof_note": "same pinned buffers, one cudaMemcpyAsync each, H2D and D2H on two streams, no compute",
-                "max_abs_vs_device_path": e2e_maxdiff},
+                "max_abs_vs_device_path": e2e_maxdiff,
+                "fp16_buffers": (dict(e2e16, value=flops_all / (e2e16["ms_per_step"] / 1e3) / 1e12, unit="TFLOP/s") if e2e16 else None)},
         "parity": parity,
         "signed_inputs": signed,
         "gpu_launches": int(launches),
@@ -539,6 +558,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-signed", action="store_true", help="skip the extra timing on signed inputs")
+    ap.add_argument("--no-e2e16", action="store_true", help="skip the fp16-host-buffer variant of the e2e measurement")
     ap.add_argument("--no-c5", action="store_true", help="N>1: skip the C5 strong-scaling measurement")
     ap.add_argument("--scales", default="block", choices=["head", "block", "tensor"],
                     help="granularity of the dynamic INT8 scales (block = the reference's 32-row tiles)")

@@ -95,6 +95,9 @@ int qmha_forward_ex(const qmha_args* a);   /* asynchronous, stream-ordered like 
  * shape — synchronous on return.  gran -1 = default for the shape.  This is what bench.py's `e2e` times. */
 int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, int B, int N,
                       int d_model, int h, int kernel, int gran);
+/* The same with fp16 / bf16 host buffers (QMHA_DTYPE_*): a 16-bit caller moves half the bytes over PCIe. */
+int qmha_forward_host_ex(const void* Q, const void* K, const void* V, void* O, int B, int N, int d_model, int h,
+                         int kernel, int gran, int in_dtype, int out_dtype);
 
 /* ---- operand preparation (kernel (a)) ------------------------------------------------------
  * Internal operand layout ("prepared" tensors), u = b*h + head:

@@ -41,6 +41,7 @@ def declare(L: C.CDLL) -> C.CDLL:
     L.solve.restype = None
     L.qmha_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
     L.qmha_forward_host.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i]
+    L.qmha_forward_host_ex.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i]
     L.qmha_workspace_dims.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
     L.qmha_quantize_qkv.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp]
     L.qmha_convert_qkv_f16.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
@@ -226,13 +227,13 @@ def flash_solve_ptr(q_ptr: int, k_ptr: int, v_ptr: int, out_ptr: int, N: int, d_
 
 
 def forward_host(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=None):
-    """Host (CPU, ideally pinned) fp32 tensors in, host tensor out; copies are pipelined over
-    (batch entry, head group) chunks inside."""
+    """Host (CPU, ideally pinned) fp32 / fp16 / bf16 tensors in, host tensor out (dtype of `out`, default that of
+    Q); copies are pipelined over (batch entry, head group) chunks inside."""
     torch = _torch()
     B, N, d_model = _shape3(Q)
     out = torch.empty_like(Q) if out is None else out
-    _check(lib().qmha_forward_host(Q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr(), B, N, d_model,
-                                   num_heads, kernel_id(kernel), gran))
+    _check(lib().qmha_forward_host_ex(Q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr(), B, N, d_model,
+                                      num_heads, kernel_id(kernel), gran, _dtype_id(Q.dtype), _dtype_id(out.dtype)))
     return out
 
 

@@ -743,8 +743,19 @@ void solve(const float* Q, const float* K, const float* V, float* output, int N,
 // a head group is a strided 2-D region of the [N, d_model] matrices (cudaMemcpy2DAsync), compact on the device.
 int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, int B, int N,
                       int d_model, int h, int kernel, int gran) {
+  return qmha_forward_host_ex(Q, K, V, O, B, N, d_model, h, kernel, gran, QMHA_DTYPE_F32, QMHA_DTYPE_F32);
+}
+
+int qmha_forward_host_ex(const void* Qv, const void* Kv, const void* Vv, void* Ov, int B, int N, int d_model, int h,
+                         int kernel, int gran, int in_dtype, int out_dtype) {
   const int dev = require_device();
   if (dev < 0) return 1;
+  if (!dtype_ok(in_dtype) || !dtype_ok(out_dtype)) return fail("unknown dtype (QMHA_DTYPE_F32 / F16 / BF16)");
+  const size_t isz = in_dtype == QMHA_DTYPE_F32 ? 4 : 2, osz = out_dtype == QMHA_DTYPE_F32 ? 4 : 2;
+  const char* Q = static_cast<const char*>(Qv);
+  const char* K = static_cast<const char*>(Kv);
+  const char* V = static_cast<const char*>(Vv);
+  char* O = static_cast<char*>(Ov);
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   if (!kernel_ok(kernel)) return fail("unknown kernel id");
@@ -755,8 +766,8 @@ int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, 
   // at least 512 bytes per 2-D copy line, at most ~64 MB of input per tensor and chunk.
   int hg = h;
   {
-    const size_t head_bytes = (size_t)N * d * 4;
-    const int min_heads = std::max(1, (int)((512 + d * 4 - 1) / (d * 4)));
+    const size_t head_bytes = (size_t)N * d * isz;
+    const int min_heads = std::max(1, (int)((512 + d * isz - 1) / (d * isz)));
     int want_chunks = std::max(1, (4 + B - 1) / B);                       // per batch entry
     int by_chunks = std::max(1, h / want_chunks);
     int by_bytes = std::max(1, (int)((size_t)64 * 1024 * 1024 / std::max<size_t>(head_bytes, 1)));
@@ -798,29 +809,30 @@ int qmha_forward_host(const float* Q, const float* K, const float* V, float* O, 
   if (w->in_flight)
     for (HostSlot& sl : w->host_slots) cudaStreamWaitEvent(sl.s, w->last_use, 0);
   const RopeOpt rope = rope_from(-1, 0.f);
-  const size_t pitch_host = (size_t)d_model * 4, width = (size_t)dmg * 4;
+  const size_t pitch_in = (size_t)d_model * isz, width_in = (size_t)dmg * isz;
+  const size_t pitch_out = (size_t)d_model * osz, width_out = (size_t)dmg * osz;
   int c = 0;
   for (int b = 0; b < B; ++b) {
     for (int g = 0; g < groups; ++g, ++c) {
       const int si = c % kHostSlots;
       HostSlot& sl = w->host_slots[si];
-      const size_t off = (size_t)b * N * d_model + (size_t)g * dmg;
+      const size_t off = (size_t)b * N * d_model + (size_t)g * dmg;   // elements
       // stream order on sl.s serialises the reuse of this slot (chunk c-kHostSlots' D2H precedes c's H2D)
-      if ((e = cudaMemcpy2DAsync(sl.q, width, Q + off, pitch_host, width, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess ||
-          (e = cudaMemcpy2DAsync(sl.k, width, K + off, pitch_host, width, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess ||
-          (e = cudaMemcpy2DAsync(sl.v, width, V + off, pitch_host, width, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess)
+      if ((e = cudaMemcpy2DAsync(sl.q, width_in, Q + off * isz, pitch_in, width_in, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess ||
+          (e = cudaMemcpy2DAsync(sl.k, width_in, K + off * isz, pitch_in, width_in, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess ||
+          (e = cudaMemcpy2DAsync(sl.v, width_in, V + off * isz, pitch_in, width_in, N, cudaMemcpyHostToDevice, sl.s)) != cudaSuccess)
         return fail_cuda("H2D copy", e);
       void* Qp = (char*)w->Qp + si * qk1;
       void* Kp = (char*)w->Kp + si * qk1;
       void* Vt = (char*)w->Vt + si * vt1;
       float* sc = w->scales + si * sc1;
       unsigned* am = w->amax + si * (2 * sc1 + 64);
-      if (prepare_impl(w, sl.q, sl.k, sl.v, QMHA_DTYPE_F32, 1, N, dmg, hg, kernel, gran, rope, Qp, Kp, Vt, sc, am, sl.s))
+      if (prepare_impl(w, sl.q, sl.k, sl.v, in_dtype, 1, N, dmg, hg, kernel, gran, rope, Qp, Kp, Vt, sc, am, sl.s))
         return 1;
-      if (attention_impl(w, Qp, Kp, Vt, sc, sl.o, QMHA_DTYPE_F32, 1, N, dmg, hg, kernel, sl.s, nullptr, -1, gran,
+      if (attention_impl(w, Qp, Kp, Vt, sc, sl.o, out_dtype, 1, N, dmg, hg, kernel, sl.s, nullptr, -1, gran,
                          w->aux + si * sc1, w->vmax + si * sc1))
         return 1;
-      if ((e = cudaMemcpy2DAsync(O + off, pitch_host, sl.o, width, width, N, cudaMemcpyDeviceToHost, sl.s)) != cudaSuccess)
+      if ((e = cudaMemcpy2DAsync(O + off * osz, pitch_out, sl.o, width_out, width_out, N, cudaMemcpyDeviceToHost, sl.s)) != cudaSuccess)
         return fail_cuda("D2H copy", e);
     }
   }

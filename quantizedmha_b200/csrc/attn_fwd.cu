@@ -283,6 +283,7 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& e0, fl
 #endif
 __device__ __forceinline__ float i2f_magic(uint32_t s, int one, int idx) {
   if (QMHA_I2F == 3) return __uint_as_float(s);   // timing experiment only: no conversion at all (wrong results)
+  if (QMHA_I2F == 5) return __int2float_rn((int)s);   // I2FP: a real conversion, no magic bias in the FMA
   if (QMHA_I2F == 1 || (QMHA_I2F == 2 && (idx & 1))) {
     int r;
     asm("mad.lo.s32 %0, %1, %2, 0x4B400000;" : "=r"(r) : "r"((int)s), "r"(one));
@@ -338,7 +339,7 @@ __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t 
                                              uint64_t (&lsum)[2], int one) {
   // x = s*c - m_used.  INT8: s is an int32 with |s| < 2^22, so bits(s + 0x4B400000) is the
   // float 12582912 + s exactly and one FMA does int->float, scale and max subtraction.
-  const float bias = kInt8 ? -fmaf(kMagicF, c, m_used) : -m_used;
+  const float bias = (kInt8 && QMHA_I2F != 5) ? -fmaf(kMagicF, c, m_used) : -m_used;
   const uint64_t c2 = pack2(c, c), bias2 = pack2(bias, bias);
 #pragma unroll
   for (int i = kBegin; i < kEnd; ++i) {
@@ -405,8 +406,8 @@ template <bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2>
 __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint32_t (&p)[kHN / 2],
                                                  const StepConsts& k, float m_used, int n_valid,
                                                  uint64_t (&ls)[2], int one) {
-  const float b0 = k.lr0 - fmaf(kMagicF, k.c0, m_used);
-  const float b1 = k.lr1 - fmaf(kMagicF, k.c1, m_used);
+  const float b0 = QMHA_I2F == 5 ? k.lr0 - m_used : k.lr0 - fmaf(kMagicF, k.c0, m_used);
+  const float b1 = QMHA_I2F == 5 ? k.lr1 - m_used : k.lr1 - fmaf(kMagicF, k.c1, m_used);
   const uint64_t c2[2] = {pack2(k.c0, k.c0), pack2(k.c1, k.c1)};
   const uint64_t bias2[2] = {pack2(b0, b0), pack2(b1, b1)};
 #pragma unroll

@@ -236,6 +236,17 @@ def test_host_buffer_entry_pipelines_over_head_groups(qm, torch, oracle, kern, g
         ho = qm.forward_host(hq, hk, hv, h, kernel=kern, gran=gran)
         assert np.array_equal(ho.numpy(), dev_out.cpu().numpy()), (kern, gran_name, group)
     monkeypatch.delenv("QMHA_HOST_HEAD_GROUP", raising=False)
+    # 16-bit host buffers in and out (half the PCIe bytes): identical to the device path on the same 16-bit tensors
+    for tdt in (torch.float16, torch.bfloat16):
+        h16 = [t.to(tdt).pin_memory() for t in (hq, hk, hv)]
+        want16 = qm.forward(*(t.cuda() for t in h16), h, kernel=kern, gran=gran)
+        _sync(qm, torch)
+        got16 = qm.forward_host(*h16, h, kernel=kern, gran=gran)
+        assert got16.dtype == tdt and torch.equal(got16, want16.cpu()), (kern, gran_name, tdt)
+        got32 = qm.forward_host(*h16, h, kernel=kern, gran=gran, out=torch.empty((N, dm), dtype=torch.float32).pin_memory())
+        want32 = qm.forward(*(t.cuda() for t in h16), h, kernel=kern, gran=gran, out_dtype=torch.float32)
+        _sync(qm, torch)
+        assert torch.equal(got32, want32.cpu()), (kern, gran_name, tdt, "fp32 out")
     # batched, pageable memory, gran -1
     q3, k3, v3 = (np.stack([a, a * 0.5, a * 2.0]) for a in (q[:300], k[:300], v[:300]))
     ho = qm.forward_host(*(torch.from_numpy(a) for a in (q3, k3, v3)), h, kernel=kern, gran=-1)

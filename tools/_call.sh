@@ -1,7 +1,8 @@
 set -x
-export QMHA_STREAM_QUANT=1
-V=quantizedmha_b200/lib/variants
-timeout 600 python tools/quant_ab.py stream_c4=quantizedmha_b200/lib/libqmha.so c3=$V/libqmha_sc3.so c3r128=$V/libqmha_sc3r128.so
-unset QMHA_STREAM_QUANT
-timeout 600 python tools/quant_ab.py cluster=quantizedmha_b200/lib/libqmha.so
-timeout 600 python -m pytest tests/test_gpu_api.py -m gpu -q -x -k persistent 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_api.py -m gpu -q -x -k "host_buffer" 2>&1 | tail -3
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e16.json 2> gpurun_out/bench_e2e16.err; tail -3 gpurun_out/bench_e2e16.err
+python -c "
+import json
+d=json.load(open('gpurun_out/bench_e2e16.json'))
+print(d['e2e'])
+"
