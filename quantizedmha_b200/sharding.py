@@ -73,3 +73,71 @@ def gather_outputs(out, B: int, H: int, group=None):
             b, h = divmod(lo + j, H)
             out[b, :, h * d:(h + 1) * d] = bufs[r][j]
     return out
+
+
+def forward_sharded(Q, K, V, H: int, kernel="int8", gran: int = -1, chunks: int = 4, group=None, forward_fn=None):
+    """Sharded forward WITH a replicated result: Q, K, V [B, N, H*d] are present on every rank,
+    rank r computes only its own (batch x head) units and every rank returns the whole output.  The rank's units are
+    cut into `chunks` groups; the all-gather of a finished group (NCCL over NVLink 5 / NVSwitch for CUDA tensors) is
+    enqueued on a side stream behind an event while the next group computes, so only the last group's transfer is
+    exposed.  Never part of the attention hot path: callers that keep their shard use forward() on it directly.
+
+    forward_fn(q, k, v, heads) -> [N, heads*d] computes one slab (default: the library's forward on CUDA tensors);
+    the CPU tests inject a host implementation and run the same code over gloo."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    B, N, d = Q.shape[0], Q.shape[1], Q.shape[2] // H
+    units = B * H
+    bounds = [unit_range(units, world, r) for r in range(world)]
+    cap = max(hi - lo for lo, hi in bounds)
+    chunks = max(1, min(chunks, cap))
+    cu = -(-cap // chunks)                                # units per chunk (last chunk may be partly padding)
+    lo, hi = bounds[rank]
+    if forward_fn is None:
+        from . import binding as qb
+        forward_fn = lambda q, k, v, heads: qb.forward(q, k, v, heads, kernel=kernel, gran=gran)
+    out = torch.empty_like(Q)
+    cuda = Q.is_cuda
+    comm = torch.cuda.Stream(device=Q.device) if cuda else None
+    pending = []
+    for c in range(chunks):
+        mine = Q.new_zeros((cu, N, d))
+        j0, j1 = c * cu, min((c + 1) * cu, hi - lo)        # this rank's unit offsets in the chunk
+        u = lo + j0
+        while u < lo + j1:                                 # slabs (b, h0..h1) inside the chunk
+            b, h0 = divmod(u, H)
+            h1 = min(H, h0 + (lo + j1 - u))
+            sl = [slab_view(t, b, h0, h1, H).contiguous() for t in (Q, K, V)]
+            o = forward_fn(sl[0], sl[1], sl[2], h1 - h0)   # [N, (h1-h0)*d]
+            slab_view(out, b, h0, h1, H).copy_(o)
+            mine[u - lo - j0:u - lo - j0 + (h1 - h0)] = o.reshape(N, h1 - h0, d).permute(1, 0, 2)
+            u += h1 - h0
+        recv = Q.new_empty((world * cu, N, d))
+        if cuda:
+            ready = torch.cuda.Event()
+            ready.record()
+            comm.wait_event(ready)
+            with torch.cuda.stream(comm):
+                work = dist.all_gather_into_tensor(recv, mine, group=group, async_op=True)
+            mine.record_stream(comm)
+            recv.record_stream(comm)
+        else:                                              # CPU tensors (gloo, tests): list form of the same collective
+            recv = [torch.empty_like(mine) for _ in range(world)]
+            work = dist.all_gather(recv, mine, group=group, async_op=True)
+        pending.append((c, recv, work))
+    for c, recv, work in pending:
+        work.wait()                                        # CUDA: makes the current stream wait for the collective
+        for r in range(world):
+            if r == rank:
+                continue
+            rlo, rhi = bounds[r]
+            block = recv[r] if isinstance(recv, list) else recv[r * cu:(r + 1) * cu]
+            j, jend = c * cu, min((c + 1) * cu, rhi - rlo)
+            while j < jend:                                # one strided copy per (batch, head range) slab
+                b, h0 = divmod(rlo + j, H)
+                h1 = min(H, h0 + (jend - j))
+                seg = block[j - c * cu:j - c * cu + (h1 - h0)]          # [heads, N, d]
+                out[b, :, h0 * d:h1 * d] = seg.permute(1, 0, 2).reshape(N, (h1 - h0) * d)
+                j += h1 - h0
+    return out

@@ -93,7 +93,7 @@ import os, sys
 sys.path.insert(0, {root!r})
 import numpy as np, torch, torch.distributed as dist
 from oracle import load_oracle
-from quantizedmha_b200.sharding import shard_slabs, slab_view, gather_outputs
+from quantizedmha_b200.sharding import shard_slabs, slab_view, gather_outputs, forward_sharded
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 orc = load_oracle()
@@ -115,6 +115,11 @@ assert np.array_equal(t.numpy(), full), "sharded result differs from the unshard
 # the optional output gather (SURVEY 8f row 4): every rank ends up with the whole tensor
 g = gather_outputs(torch.from_numpy(mine.copy()), B, H)
 assert np.array_equal(g.numpy(), full), "gathered result differs from the unsharded oracle"
+# sharded forward with the chunked, overlapped gather (same code path as on NCCL; the CPU oracle computes the slabs)
+fwd = lambda a, b, c, heads: torch.from_numpy(orc.mha(a.numpy(), b.numpy(), c.numpy(), heads, threads=1))
+for chunks in (1, 2, 5):
+    o = forward_sharded(torch.from_numpy(q), torch.from_numpy(k), torch.from_numpy(v), H, chunks=chunks, forward_fn=fwd)
+    assert np.array_equal(o.numpy(), full), f"forward_sharded(chunks={{chunks}}) differs from the unsharded oracle"
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)

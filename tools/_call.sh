@@ -1,8 +1,4 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_api.py -m gpu -q -x -k "host_buffer" 2>&1 | tail -3
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e16.json 2> gpurun_out/bench_e2e16.err; tail -3 gpurun_out/bench_e2e16.err
-python -c "
-import json
-d=json.load(open('gpurun_out/bench_e2e16.json'))
-print(d['e2e'])
-"
+O=gpurun_out/r02; mkdir -p $O
+N=$(nvidia-smi -L | wc -l)
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tools/nccl_gather_check.py > $O/nccl_gather_${N}gpu.txt 2>&1; tail -8 $O/nccl_gather_${N}gpu.txt

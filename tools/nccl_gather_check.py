@@ -8,7 +8,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import quantizedmha_b200 as qm
-from quantizedmha_b200.sharding import shard_slabs, slab_view, gather_outputs
+from quantizedmha_b200.sharding import shard_slabs, slab_view, gather_outputs, forward_sharded
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -32,6 +32,39 @@ for kernel, gran in (("int8", qm.GRAN_BLOCK), ("int8", qm.GRAN_HEAD), ("f16", qm
     ok = ok and same
     if rank == 0:
         print(f"{kernel} gran={gran}: gathered == single-GPU forward: {same}", flush=True)
+# sharded forward with the chunked gather that overlaps the transfer of finished units with the next units' compute
+for chunks in (1, 3):
+    out = forward_sharded(q, k, v, H, kernel="int8", gran=qm.GRAN_BLOCK, chunks=chunks)
+    full = qm.forward(q, k, v, H, kernel="int8", gran=qm.GRAN_BLOCK)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(out, full))
+    ok = ok and same
+    if rank == 0:
+        print(f"forward_sharded(chunks={chunks}) == single-GPU forward: {same}", flush=True)
+# timing at a BASELINE-sized shape: 8 batch entries of C4 split over the ranks, result replicated on every rank
+Bt, Ht, Nt, dt = 8, 32, 8192, 128
+gen = torch.Generator(device=dev).manual_seed(99)
+qt, kt, vt = (torch.rand((Bt, Nt, Ht * dt), device=dev, generator=gen) for _ in range(3))
+def timed(fn, reps=3):
+    fn(); torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+def compute_only():
+    for (b, h0, h1) in shard_slabs(Bt, Ht, world, rank):
+        sl = [slab_view(t, b, h0, h1, Ht).contiguous() for t in (qt, kt, vt)]
+        qm.forward(*sl, h1 - h0, kernel="int8", gran=qm.GRAN_BLOCK)
+t_comp = timed(compute_only)
+t_1 = timed(lambda: forward_sharded(qt, kt, vt, Ht, kernel="int8", gran=qm.GRAN_BLOCK, chunks=1))
+t_4 = timed(lambda: forward_sharded(qt, kt, vt, Ht, kernel="int8", gran=qm.GRAN_BLOCK, chunks=4))
+t_8 = timed(lambda: forward_sharded(qt, kt, vt, Ht, kernel="int8", gran=qm.GRAN_BLOCK, chunks=8))
+if rank == 0:
+    gb = Bt * Nt * Ht * dt * 4 / 1e9
+    print(f"C4 split over {world} ranks, replicated {gb:.2f} GB result: own slabs only {t_comp:.2f} ms; "
+          f"compute + gather, 1 chunk (no overlap) {t_1:.2f} ms; 4 chunks {t_4:.2f} ms; 8 chunks {t_8:.2f} ms", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
