@@ -48,6 +48,27 @@ def test_kernel_name_aliases(qm):
         qm.kernel_id("no_such_kernel")
 
 
+def test_extended_entry_host_logic(qm):
+    """qmha_forward_ex argument block (struct_size guard, defaults), the BF16 kernel names and the choice of the
+    scale granularity for a shape — host logic only, no device needed."""
+    import ctypes as C
+    L = qm.lib()
+    assert qm.kernel_id("bf16") == qm.KERNEL_BF16 and qm.kernel_id("fa_b200_bf16") == qm.KERNEL_BF16
+    a = qm.QmhaArgs()
+    L.qmha_args_init(C.byref(a))
+    assert a.struct_size == C.sizeof(qm.QmhaArgs), "ctypes mirror of qmha_args is out of step with include/qmha.h"
+    assert (a.kernel, a.gran, a.rope, a.variant, a.in_dtype, a.out_dtype) == (-1, -1, -1, -1, qm.DTYPE_F32, qm.DTYPE_F32)
+    a.struct_size = 8
+    assert L.qmha_forward_ex(C.byref(a)) != 0 and b"struct_size" in L.qmha_last_error()
+    assert L.qmha_forward_ex(None) != 0
+    # block scales while the per-block table of one unit fits in shared memory behind the tiles, per-head beyond
+    assert L.qmha_granularity_for(8192, 4096, 32) == qm.GRAN_BLOCK
+    assert L.qmha_granularity_for(16384, 4096, 32) == qm.GRAN_BLOCK
+    assert L.qmha_granularity_for(68608, 128, 1) == qm.GRAN_BLOCK and L.qmha_granularity_for(68609, 128, 1) == qm.GRAN_HEAD
+    assert L.qmha_granularity_for(512, 30, 2) == qm.GRAN_HEAD          # d = 15: scalar two-pass path
+    assert L.qmha_default_granularity(4096, 32) == qm.GRAN_BLOCK
+
+
 def test_workspace_dims_and_shape_validation(qm):
     assert qm.workspace_dims(8192, 4096, 32) == (8192, 128)
     assert qm.workspace_dims(50, 64, 8) == (256, 32)
