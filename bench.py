@@ -32,6 +32,7 @@ WORKLOADS = {
     "c2": (1, 32, 8192, 32, "f16", "weak"),      # reference default config.h shape, FP16 anchor
     "c4f16": (8, 32, 8192, 128, "f16", "weak"),  # FP16 anchor at the headline shape
     "c4bf16": (8, 32, 8192, 128, "bf16", "weak"),  # BF16 anchor at the headline shape
+    "c4pv8": (8, 32, 8192, 128, "int8_pv8", "weak"),  # INT8 kernel with INT8 P.V (the reference's P semantics), opt-in mode
     "c5": (32, 32, 16384, 128, "int8", "strong"),  # long-context sweep: units split over ranks
 }
 N_SM, MUFU_PER_SM_CLK = 148, 16   # B200: 148 SMs, 16 ex2 per SM per clock (4 per sub-partition)
@@ -196,10 +197,11 @@ class Job:
         self.out = torch.empty(shape, device=dev)
         n_pad, d_pad = qm.workspace_dims(N, self.dm, H)
         units = Bl * H
-        elt = torch.int8 if kernel == "int8" else torch.float16   # bf16 operands are 2 bytes as well
+        self.int8 = kernel in ("int8", "int8_pv8")
+        elt = torch.int8 if self.int8 else torch.float16   # bf16 operands are 2 bytes as well
         self.Qp = torch.empty((units, n_pad, d_pad), dtype=elt, device=dev)
         self.Kp = torch.empty_like(self.Qp)
-        self.Vt = torch.empty((units, d_pad, n_pad), dtype=torch.float16, device=dev)
+        self.Vt = torch.empty((units, d_pad, n_pad), dtype=torch.int8 if kernel == "int8_pv8" else torch.float16, device=dev)
         self.sc = torch.empty((3, units, n_pad // 32) if gran == qm.GRAN_BLOCK else (3, units), dtype=torch.float32, device=dev)
         self.stream = torch.cuda.current_stream()
         self.sp = int(self.stream.cuda_stream)
@@ -216,10 +218,10 @@ class Job:
             raise RuntimeError(self.L.qmha_last_error().decode())
 
     def prep(self):
-        if self.kernel == "int8":
-            self.chk(self.L.qmha_quantize_qkv(self.tq.data_ptr(), self.tk.data_ptr(), self.tv.data_ptr(), self.Bl, self.N,
-                                              self.dm, self.H, self.gran, self.Qp.data_ptr(), self.Kp.data_ptr(),
-                                              self.Vt.data_ptr(), self.sc.data_ptr(), self.sp))
+        if self.int8:
+            self.chk(self.L.qmha_quantize_qkv_k(self.tq.data_ptr(), self.tk.data_ptr(), self.tv.data_ptr(), 0, self.Bl, self.N,
+                                                self.dm, self.H, self.kid, self.gran, -1, 0.0, self.Qp.data_ptr(),
+                                                self.Kp.data_ptr(), self.Vt.data_ptr(), self.sc.data_ptr(), self.sp))
         else:
             self.chk(self.L.qmha_convert_qkv_16(self.tq.data_ptr(), self.tk.data_ptr(), self.tv.data_ptr(), 0, self.Bl, self.N,
                                                 self.dm, self.H, self.kid, -1, 0.0, self.Qp.data_ptr(), self.Kp.data_ptr(),
@@ -227,7 +229,7 @@ class Job:
 
     def attn(self):
         self.chk(self.L.qmha_attention_prepared(self.Qp.data_ptr(), self.Kp.data_ptr(), self.Vt.data_ptr(),
-                                                self.sc.data_ptr() if self.kernel == "int8" else None, self.out.data_ptr(),
+                                                self.sc.data_ptr() if self.int8 else None, self.out.data_ptr(),
                                                 self.Bl, self.N, self.dm, self.H, self.kid, self.gran, self.sp))
 
     def time(self, steps, warmup, barrier, attn_only=False):
@@ -281,7 +283,7 @@ class Job:
             num += float(((got - ref) ** 2).sum()); den += float((ref ** 2).sum())
             rows_total += len(rows)
         rel = (num / max(den, 1e-300)) ** 0.5
-        tol_abs, tol_rel = {"int8": (2e-2, 1e-2), "f16": (2e-3, None), "bf16": (1e-2, None)}[self.kernel]
+        tol_abs, tol_rel = {"int8": (2e-2, 1e-2), "int8_pv8": (2e-2, 1e-2), "f16": (2e-3, None), "bf16": (1e-2, None)}[self.kernel]
         ok = mx <= tol_abs and (tol_rel is None or rel <= tol_rel)
         return {"max_abs": mx, "rel_l2": rel, "rows": int(rows_total), "units": len(units), "ok": bool(ok),
                 "checker": "oracle.mha_head_rows float64 (generate_golden.cpp:69-90 per-row routine), all N keys per row",
@@ -413,7 +415,8 @@ def run_native(args):
 
     # ---- the same kernel on signed inputs (0.5*N(0,1)): the lazy O-rescale path really runs there
     signed = None
-    if kernel == "int8" and not args.no_signed:
+    is_int8 = kernel in ("int8", "int8_pv8")
+    if is_int8 and not args.no_signed:
         gen = torch.Generator(device=dev); gen.manual_seed(4242 + rank)
         job.fill("normal", gen)
         s_ms, s_attn, s_prep, _ = job.time(min(K, 5), 1, barrier)
@@ -450,8 +453,8 @@ def run_native(args):
     E = Bl * N * dm
     # quantise pass: SURVEY §8(d) algorithmic bytes = one fp32 read + one int8 write of Q, K, V = 15*E; the kernel
     # writes the V codes as fp16 (the P.V MMA is 16-bit), i.e. 16*E actually moved.  FP16/BF16: 12*E + 6*E.
-    prep_alg = 15 * E if kernel == "int8" else 18 * E
-    prep_act = 16 * E if kernel == "int8" else 18 * E
+    prep_alg = 15 * E if is_int8 else 18 * E
+    prep_act = (16 * E if kernel == "int8" else 15 * E) if is_int8 else 18 * E
     pk = peaks()
     traffic = None
     for rnd in ("r02", "r01"):   # per-launch DRAM traffic from one `ncu --set full` capture of this command
@@ -468,7 +471,7 @@ def run_native(args):
     # region): with the measured bf16 rate it gives the time-weighted ceiling of a kernel whose Q.K^T half
     # runs on the INT8 pipe and whose P.V half runs on the 16-bit pipe.
     int8_gemm = None
-    if rank == 0 and kernel == "int8":
+    if rank == 0 and is_int8:
         try:
             ga = torch.randint(-127, 127, (8192, 8192), dtype=torch.int8, device=dev)
             gb = torch.randint(-127, 127, (8192, 8192), dtype=torch.int8, device=dev).t()
@@ -484,7 +487,11 @@ def run_native(args):
             int8_gemm = None
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     mufu_bound = N_SM * MUFU_PER_SM_CLK * sm_mhz * 1e6 * 4.0 * d / 1e12   # one ex2 per score element = 4d FLOPs
-    if kernel == "int8":
+    if kernel == "int8_pv8":
+        roof_peak = int8_gemm or 4500.0
+        peak_src = ("INT8 GEMM rate measured live on this box (torch._int_mm 8192^3): both GEMMs of this mode run on the INT8 pipe"
+                    if int8_gemm else "nominal 4500 (live INT8 GEMM measurement unavailable)")
+    elif kernel == "int8":
         mixed_peak = 2.0 / (1.0 / int8_gemm + 1.0 / pk["bf16_sustained"]) if int8_gemm else 2.0 / (1.0 / 4500.0 + 1.0 / pk["bf16_sustained"])
         roof_peak = mixed_peak
         peak_src = (f"harmonic mean (half of the FLOPs each) of the INT8 GEMM rate measured live on this box "
@@ -493,18 +500,19 @@ def run_native(args):
     else:
         roof_peak = pk["bf16_sustained"]
         peak_src = f"{pk['src']} dense bf16 cuBLAS GEMM, sustained (kernel timed inside the step loop)"
-    operand_bytes = E * (1 + 1 + 2) + E * 4 if kernel == "int8" else E * 6 + E * 4
+    operand_bytes = (E * (1 + 1 + (2 if kernel == "int8" else 1)) + E * 4) if is_int8 else E * 6 + E * 4
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-        "dtype": {"int8": "s8*s8->s32 (Q.K^T), f16*f16->f32 (P.V), f32 softmax", "f16": "f16*f16->f32, f32 softmax",
+        "dtype": {"int8": "s8*s8->s32 (Q.K^T), f16*f16->f32 (P.V), f32 softmax",
+                  "int8_pv8": "s8*s8->s32 (Q.K^T), u8*s8->s32 (P.V), f32 softmax", "f16": "f16*f16->f32, f32 softmax",
                   "bf16": "bf16*bf16->f32, f32 softmax"}[kernel],
         "data": "synthetic U[0,1) (inputs/data.cu distribution), random on device",
         "config": {"workload": f"{args.workload}: B={B}{' per GPU' if scaling == 'weak' and world > 1 else ''} H={H} N={N} d={d} "
                                f"kernel={kernel} scales={args.scales}", "l2": f"inputs+outputs {4 * Bl * N * dm * 4 / 1e9:.2f} GB per GPU vs 126 MB L2 (no flush needed when larger)",
                    "parallelism": f"(batch x head) units sharded over {world} GPU(s), no collective"},
         "attn_ms": attn_ms, "attn_tflops_per_gpu": attn_tflops, "prep_ms": prep_ms,
-        "prep": {"kernel": "block_quantize_kernel" if (kernel == "int8" and gran == qm.GRAN_BLOCK) else "quantise / convert",
+        "prep": {"kernel": "block_quantize_kernel" if (is_int8 and gran == qm.GRAN_BLOCK) else "quantise / convert",
                  "bound": "hbm", "peak_gbs": pk["hbm"], "algorithmic_bytes_15E": prep_alg, "moved_bytes_16E": prep_act,
                  "gbs_algorithmic": prep_alg / (prep_ms / 1e3) / 1e9, "frac_algorithmic": prep_alg / (prep_ms / 1e3) / 1e9 / pk["hbm"],
                  "gbs_moved": prep_act / (prep_ms / 1e3) / 1e9, "frac_moved": prep_act / (prep_ms / 1e3) / 1e9 / pk["hbm"]},
@@ -512,7 +520,7 @@ def run_native(args):
                      "unit": "TFLOP/s", "frac": attn_tflops / roof_peak, "traffic": traffic,
                      "traffic_note": f"DRAM read+write bytes per launch from the ncu --set full capture under profiles/; algorithmic operand+output bytes = {operand_bytes}",
                      "peak_src": peak_src,
-                     "frac_of_nominal_int8_4500": attn_tflops / 4500.0 if kernel == "int8" else None,
+                     "frac_of_nominal_int8_4500": attn_tflops / 4500.0 if is_int8 else None,
                      "frac_of_bf16_sustained": attn_tflops / pk["bf16_sustained"],
                      "int8_gemm_tflops_measured": int8_gemm,
                      "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": attn_tflops / mufu_bound,

@@ -33,6 +33,10 @@ extern "C" {
 #define QMHA_KERNEL_INT8 0 /* Q·K^T tcgen05 kind::i8, P·V kind::f16; replaces fa_tc_int8_a/b   */
 #define QMHA_KERNEL_F16 1  /* Q·K^T and P·V tcgen05 kind::f16; replaces fa_tc_v1a..v2b, fa, unfused */
 #define QMHA_KERNEL_BF16 2 /* same pipeline with bf16 operands (Q, K, P, V rounded to bf16), fp32 accumulation */
+#define QMHA_KERNEL_INT8_PV8 3 /* INT8 kernel with the reference's P.V semantics (fa_tc_int8_b.cu:359-371): P quantised to
+                                  8-bit codes (static scale) and multiplied with the int8 V codes on the INT8 pipe, int32
+                                  accumulation.  Opt-in: coarser than fp16 P for long-tailed rows and not faster here
+                                  (DESIGN.md §4.2.1).  Names: "int8_pv8", "fa_b200_int8_pv8". */
 
 /* Element types of Q, K, V and of the output in the extended entries (the reference's API is fp32 only). */
 #define QMHA_DTYPE_F32 0
@@ -119,6 +123,12 @@ int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int
 int qmha_quantize_qkv_ex(const void* Q, const void* K, const void* V, int in_dtype, int B, int N, int d_model,
                          int h, int gran, int rope, float rope_base, int8_t* Qp, int8_t* Kp, uint16_t* Vt,
                          float* scales, void* stream);
+
+/* Same, operands for `kernel` = QMHA_KERNEL_INT8 (V codes stored as fp16) or QMHA_KERNEL_INT8_PV8 (Vt = int8 codes
+ * [B*h, d_pad, n_pad]). */
+int qmha_quantize_qkv_k(const void* Q, const void* K, const void* V, int in_dtype, int B, int N, int d_model,
+                        int h, int kernel, int gran, int rope, float rope_base, int8_t* Qp, int8_t* Kp, void* Vt,
+                        float* scales, void* stream);
 
 /* fp32 -> fp16 operand conversion for the F16 variant (fa_tc_v1a.cu:267,321,348 convert on
  * load; here it is one HBM-bound pre-pass).  Qp/Kp are fp16 stored as uint16_t. */

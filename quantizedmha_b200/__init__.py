@@ -17,6 +17,7 @@ from .binding import (  # noqa: F401
     KERNEL_BF16,
     KERNEL_F16,
     KERNEL_INT8,
+    KERNEL_INT8_PV8,
     attention_prepared,
     convert_qkv_f16,
     flash_solve,

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 from typing import Optional, Tuple
 
-KERNEL_INT8, KERNEL_F16, KERNEL_BF16 = 0, 1, 2
+KERNEL_INT8, KERNEL_F16, KERNEL_BF16, KERNEL_INT8_PV8 = 0, 1, 2, 3
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 GRAN_TENSOR, GRAN_HEAD, GRAN_BLOCK = 0, 1, 2
 
@@ -49,6 +49,7 @@ def declare(L: C.CDLL) -> C.CDLL:
     L.qmha_quantize_static.argtypes = [vp, C.c_int64, f, f, vp, vp]
     L.qmha_attention_prepared.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     L.qmha_quantize_qkv_ex.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, f, vp, vp, vp, vp, vp]
+    L.qmha_quantize_qkv_k.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, f, vp, vp, vp, vp, vp]
     L.qmha_convert_qkv_16.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, f, vp, vp, vp, vp]
     L.qmha_attention_prepared_ex.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     L.qmha_forward_ex.argtypes = [C.POINTER(QmhaArgs)]
@@ -237,9 +238,11 @@ def forward_host(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, 
     return out
 
 
-def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None, rope=None, rope_base: float = 10000.0):
+def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None, rope=None, rope_base: float = 10000.0,
+                 kernel="int8"):
     """Kernel (a).  Returns (Qp int8 [B*h,n_pad,d_pad], Kp, Vt fp16 [B*h,d_pad,n_pad], scales [3,B*h]
-    or, for GRAN_BLOCK, [3,B*h,n_pad/32]).  Inputs: float32, float16 or bfloat16."""
+    or, for GRAN_BLOCK, [3,B*h,n_pad/32]).  Inputs: float32, float16 or bfloat16.  kernel="int8_pv8": Vt holds
+    the int8 codes themselves (int8 tensor) for the INT8 P.V mode."""
     torch = _torch()
     _check_inputs(Q, K, V, allow16=True)
     Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
@@ -248,15 +251,16 @@ def quantize_qkv(Q, K, V, num_heads: int, gran: int = GRAN_HEAD, stream=None, ro
     u = B * num_heads
     Qp = torch.empty((u, n_pad, d_pad), dtype=torch.int8, device=Q.device)
     Kp = torch.empty_like(Qp)
-    Vt = torch.empty((u, d_pad, n_pad), dtype=torch.float16, device=Q.device)
+    kid = kernel_id(kernel)
+    Vt = torch.empty((u, d_pad, n_pad), dtype=torch.int8 if kid == KERNEL_INT8_PV8 else torch.float16, device=Q.device)
     if gran == GRAN_BLOCK:
         scales = torch.empty((3, u, n_pad // 32), dtype=torch.float32, device=Q.device)
     else:
         scales = torch.empty((3, u), dtype=torch.float32, device=Q.device)
-    _check(lib().qmha_quantize_qkv_ex(Q.data_ptr(), K.data_ptr(), V.data_ptr(), _dtype_id(Q.dtype), B, N, d_model,
-                                      num_heads, gran, -1 if rope is None else int(bool(rope)), float(rope_base),
-                                      Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), scales.data_ptr(),
-                                      _stream_ptr(stream)))
+    _check(lib().qmha_quantize_qkv_k(Q.data_ptr(), K.data_ptr(), V.data_ptr(), _dtype_id(Q.dtype), B, N, d_model,
+                                     num_heads, kid, gran, -1 if rope is None else int(bool(rope)), float(rope_base),
+                                     Qp.data_ptr(), Kp.data_ptr(), Vt.data_ptr(), scales.data_ptr(),
+                                     _stream_ptr(stream)))
     return Qp, Kp, Vt, scales
 
 

@@ -307,7 +307,8 @@ int get_rope_table(Workspace* w, int N, int d, float base, const float2** out) {
 }
 
 bool dtype_ok(int dt) { return dt == QMHA_DTYPE_F32 || dt == QMHA_DTYPE_F16 || dt == QMHA_DTYPE_BF16; }
-bool kernel_ok(int k) { return k == QMHA_KERNEL_INT8 || k == QMHA_KERNEL_F16 || k == QMHA_KERNEL_BF16; }
+bool kernel_ok(int k) { return k == QMHA_KERNEL_INT8 || k == QMHA_KERNEL_F16 || k == QMHA_KERNEL_BF16 || k == QMHA_KERNEL_INT8_PV8; }
+bool is_int8(int k) { return k == QMHA_KERNEL_INT8 || k == QMHA_KERNEL_INT8_PV8; }
 
 struct RopeOpt {
   bool on = false;
@@ -333,8 +334,9 @@ int prepare_impl(Workspace* w, const void* Q, const void* K, const void* V, int 
   qmha::PrepareArgs a;
   a.Q = Q; a.K = K; a.V = V; a.in_dtype = in_dtype; a.scales = scales; a.Qp = Qp; a.Kp = Kp; a.Vt = Vt;
   a.B = B; a.N = N; a.H = h; a.d = d; a.n_pad = n_pad; a.d_pad = d_pad;
-  a.int8 = kernel == QMHA_KERNEL_INT8;
+  a.int8 = is_int8(kernel);
   a.bf16 = kernel == QMHA_KERNEL_BF16;
+  a.v8 = kernel == QMHA_KERNEL_INT8_PV8;
   a.stream = stream;
   if (rope.on) {
     if ((d & 7) != 0) return fail("fused RoPE needs a head dimension that is a multiple of 8");
@@ -353,7 +355,7 @@ int prepare_impl(Workspace* w, const void* Q, const void* K, const void* V, int 
     // Per-(batch, head) scales: one cluster kernel reads the inputs from HBM once.  Per-tensor
     // scales need a global maximum first and keep the two-pass path (as does an odd head dim).
     static const bool two_pass_env = getenv("QMHA_TWO_PASS_QUANT") != nullptr;
-    if (gran == QMHA_GRAN_HEAD && (d & 3) == 0 && !two_pass_env) {
+    if (gran == QMHA_GRAN_HEAD && (d & 3) == 0 && !two_pass_env && !a.v8) {   // (INT8 P.V: block kernel or two-pass path)
       // cluster kernel by default; QMHA_STREAM_QUANT=1: the persistent-grid variant (same results, same speed)
       if (getenv("QMHA_STREAM_QUANT") == nullptr) {
         if ((e = qmha::launch_fused_quantize(a)) != cudaSuccess) return fail_cuda("fused quantise launch", e);
@@ -396,8 +398,9 @@ int attention_impl(Workspace* w, const void* Qp, const void* Kp, const void* Vt,
   a.Qp = Qp; a.Kp = Kp; a.Vt = Vt; a.scales = scales; a.O = O; a.out_dtype = out_dtype;
   a.error_flag = w->error_flag; a.error_host = w->error_host_dev; a.launch_id = next_launch_id();
   a.B = B; a.N = N; a.H = h; a.d = d; a.n_pad = n_pad; a.d_pad = d_pad;
-  a.int8 = kernel == QMHA_KERNEL_INT8;
+  a.int8 = is_int8(kernel);
   a.bf16 = kernel == QMHA_KERNEL_BF16;
+  a.pv8 = kernel == QMHA_KERNEL_INT8_PV8;
   a.stream = stream;
   a.trace = trace;
   a.cycles = cycles;
@@ -435,7 +438,7 @@ int forward_device(const qmha_args& a) {
   int d, n_pad, d_pad;
   if (check_shape(a.B, a.N, a.d_model, a.h, &d, &n_pad, &d_pad)) return 1;
   const size_t units = (size_t)a.B * a.h;
-  const size_t elt = a.kernel == QMHA_KERNEL_INT8 ? 1 : 2;
+  const size_t elt = is_int8(a.kernel) ? 1 : 2;
   Workspace* w;
   std::unique_lock<std::mutex> call_lock;
   if (get_workspace(dev, units * n_pad * d_pad * elt, units * n_pad * d_pad * 2,
@@ -488,6 +491,7 @@ int qmha_kernel_from_name(const char* name) {
       n == "fa_tc_v2b" || n == "fa_tc" || n == "fa_warps")
     return QMHA_KERNEL_F16;
   if (n == "bf16" || n == "fa_b200_bf16") return QMHA_KERNEL_BF16;
+  if (n == "int8_pv8" || n == "fa_b200_int8_pv8") return QMHA_KERNEL_INT8_PV8;
   return -1;
 }
 
@@ -513,7 +517,7 @@ int qmha_granularity_for(int N, int d_model, int h) { return default_granularity
 
 const char* qmha_get_kernel(void) {
   const int k = resolve_default_kernel();
-  return k == QMHA_KERNEL_INT8 ? "int8" : (k == QMHA_KERNEL_BF16 ? "bf16" : "f16");
+  return k == QMHA_KERNEL_INT8 ? "int8" : (k == QMHA_KERNEL_BF16 ? "bf16" : (k == QMHA_KERNEL_INT8_PV8 ? "int8_pv8" : "f16"));
 }
 
 int qmha_workspace_dims(int N, int d_model, int h, int* n_pad, int* d_pad) {
@@ -534,6 +538,13 @@ int qmha_quantize_qkv(const float* Q, const float* K, const float* V, int B, int
 int qmha_quantize_qkv_ex(const void* Q, const void* K, const void* V, int in_dtype, int B, int N, int d_model,
                          int h, int gran, int rope, float rope_base, int8_t* Qp, int8_t* Kp, uint16_t* Vt,
                          float* scales, void* stream) {
+  return qmha_quantize_qkv_k(Q, K, V, in_dtype, B, N, d_model, h, QMHA_KERNEL_INT8, gran, rope, rope_base, Qp, Kp, Vt, scales, stream);
+}
+
+int qmha_quantize_qkv_k(const void* Q, const void* K, const void* V, int in_dtype, int B, int N, int d_model,
+                        int h, int kernel, int gran, int rope, float rope_base, int8_t* Qp, int8_t* Kp, void* Vt,
+                        float* scales, void* stream) {
+  if (!is_int8(kernel)) return fail("qmha_quantize_qkv_k: kernel must be QMHA_KERNEL_INT8 or QMHA_KERNEL_INT8_PV8");
   const int dev = require_device();
   if (dev < 0) return 1;
   if (gran != QMHA_GRAN_TENSOR && gran != QMHA_GRAN_HEAD && gran != QMHA_GRAN_BLOCK) return fail("unknown scale granularity");
@@ -542,7 +553,7 @@ int qmha_quantize_qkv_ex(const void* Q, const void* K, const void* V, int in_dty
   if (get_workspace(dev, 0, 0, (size_t)3 * B * h, &w, &call_lock)) return 1;
   WorkspaceUse use;
   use.begin(w, std::move(call_lock), (cudaStream_t)stream);
-  if (prepare_impl(w, Q, K, V, in_dtype, B, N, d_model, h, QMHA_KERNEL_INT8, gran, rope_from(rope, rope_base),
+  if (prepare_impl(w, Q, K, V, in_dtype, B, N, d_model, h, kernel, gran, rope_from(rope, rope_base),
                    Qp, Kp, Vt, scales, w->amax, (cudaStream_t)stream))
     return 1;
   g_err.clear();
@@ -760,7 +771,7 @@ int qmha_forward_host_ex(const void* Qv, const void* Kv, const void* Vv, void* O
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   if (!kernel_ok(kernel)) return fail("unknown kernel id");
   if (gran < 0) gran = default_granularity(N, d_model, h);
-  if (kernel == QMHA_KERNEL_INT8 && gran == QMHA_GRAN_TENSOR)
+  if (is_int8(kernel) && gran == QMHA_GRAN_TENSOR)
     return fail("qmha_forward_host pipelines over (batch, head group) chunks; use QMHA_GRAN_HEAD or QMHA_GRAN_BLOCK scales");
   // Head groups: enough chunks to overlap copies with compute (>= 4 per call when the heads allow it), rows of
   // at least 512 bytes per 2-D copy line, at most ~64 MB of input per tensor and chunk.
@@ -780,7 +791,7 @@ int qmha_forward_host_ex(const void* Qv, const void* Kv, const void* Vv, void* O
   const int groups = h / hg;
   const int dmg = hg * d;                         // d_model of one chunk on the device
   const size_t chunk = (size_t)N * dmg;           // elements per tensor and chunk
-  const size_t elt = kernel == QMHA_KERNEL_INT8 ? 1 : 2;
+  const size_t elt = is_int8(kernel) ? 1 : 2;
   const size_t qk1 = (size_t)hg * n_pad * d_pad * elt, vt1 = (size_t)hg * n_pad * d_pad * 2;
   const size_t sc1 = scale_count(hg, n_pad, gran);
   Workspace* w;

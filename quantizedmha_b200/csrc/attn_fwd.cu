@@ -85,8 +85,9 @@ constexpr float kRescaleThreshold = 4.0f;  // log2 units: P <= 2^4, well inside 
 constexpr int kMagicI2F = 0x4B400000;      // float(1.5 * 2^23): int -> float by bit tricks
 constexpr float kMagicF = 12582912.0f;
 
-template <bool kInt8, int kD>
+template <bool kInt8, int kD, bool kPv8 = false>
 struct Cfg {
+  static_assert(!kPv8 || kInt8, "INT8 P.V is a mode of the INT8 kernel");
   static constexpr int kEltQK = kInt8 ? 1 : 2;
   static constexpr int kRowBytesQK = kD * kEltQK;                       // bytes per Q/K row
   static constexpr int kAtomQK = kRowBytesQK < 128 ? kRowBytesQK : 128;  // swizzle span
@@ -94,9 +95,13 @@ struct Cfg {
   static constexpr int kTileBytesQK = kBM * kRowBytesQK;
   static constexpr int kSubBytesQK = kBM * kAtomQK;
   static constexpr int kStepsQK = kRowBytesQK / 32;                     // UMMA K steps (32 B each)
-  static constexpr int kTileBytesV = kD * kBN * 2;                      // V^T tile: kD x 128 fp16
-  static constexpr int kSubBytesV = kD * 128;                           // 64 keys x kD rows
-  static constexpr int kStepsPV = kHN / 16;                             // UMMA K steps per half-step
+  // V^T tile: kD rows x 128 keys.  fp16 (default): two 64-key sub-tiles of kD x 128 B; INT8 P.V: one sub-tile,
+  // 128 keys = 128 B per row, the second half-step starts 64 B into the row (inside the swizzle atom).
+  static constexpr int kTileBytesV = kD * kBN * (kPv8 ? 1 : 2);
+  static constexpr int kSubTilesV = kPv8 ? 1 : 2;                       // TMA boxes per tile
+  static constexpr int kSubBytesV = kD * 128;                           // one box
+  static constexpr int kHalfOffV = kPv8 ? 64 : kD * 128;                // byte offset of keys 64..127 for the descriptor
+  static constexpr int kStepsPV = kPv8 ? kHN / 32 : kHN / 16;           // UMMA K steps per half-step
   static constexpr int kHalfBytesQK = kHN * kAtomQK;                    // byte offset of K rows 64.. in a sub-tile
   // K tiles are consumed 1.5 tiles ahead of V tiles (S runs three half-steps ahead of P·V), so the
   // K ring is one stage deeper than the V ring; each ring has its own producer warp.
@@ -116,6 +121,8 @@ struct Cfg {
             : make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kHN);
   static constexpr uint32_t kIdescPV = make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kD);
   // BF16 anchor: same kind::f16 instructions with the bf16 operand format (operands, P and V^T are bf16)
+  // INT8 P.V (QMHA_KERNEL_INT8_PV8): P as unsigned 8-bit codes from TMEM, V^T as int8, int32 accumulators
+  static constexpr uint32_t kIdescPV8 = make_idesc(kAccS32, kFmtU8, kFmtS8, kBM, kD);
   static constexpr uint32_t kIdescQKbf = make_idesc(kAccF32, kFmtBF16, kFmtBF16, kBM, kHN);
   static constexpr uint32_t kIdescPVbf = make_idesc(kAccF32, kFmtBF16, kFmtBF16, kBM, kD);
 };
@@ -332,14 +339,24 @@ __device__ __forceinline__ void i2f_pair(uint32_t s0, uint32_t s1, int one, int 
   f1 = i2f_magic(s1, one, 2 * i + 1);
 }
 
+// INT8 P.V: P goes to the tensor pipe as unsigned 8-bit codes rn(127.5 * p), p <= 2 (the lazy-rescale threshold is one
+// log2 unit in that mode).  log2(127.5) rides in the exponent bias; adding 1.5 * 2^23 leaves rn(e) in the low mantissa
+// byte (no float->int conversion, which would run on the MUFU's pipe); one PRMT packs a pair, one more a quad.
+constexpr float kLog2P8 = 6.994353436858858f;
+__device__ __forceinline__ uint32_t pack_u8x2(float e0, float e1) {
+  float m0, m1;
+  unpack2(fadd2(pack2(e0, e1), pack2(kMagicF, kMagicF)), m0, m1);
+  return __byte_perm(__float_as_uint(m0), __float_as_uint(m1), 0x0040);   // byte 0 = code(e0), byte 1 = code(e1)
+}
+
 // kPolyEvery: every kPolyEvery-th pair of the row takes the polynomial path (0 = all on MUFU).
-template <bool kInt8, bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2, bool kBf16 = false>
+template <bool kInt8, bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2, bool kBf16 = false, bool kPv8 = false>
 __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t (&p)[kHN / 2],
                                              float c, float m_used, int n_valid,
                                              uint64_t (&lsum)[2], int one) {
   // x = s*c - m_used.  INT8: s is an int32 with |s| < 2^22, so bits(s + 0x4B400000) is the
   // float 12582912 + s exactly and one FMA does int->float, scale and max subtraction.
-  const float bias = (kInt8 && QMHA_I2F != 5) ? -fmaf(kMagicF, c, m_used) : -m_used;
+  const float bias = ((kInt8 && QMHA_I2F != 5) ? -fmaf(kMagicF, c, m_used) : -m_used) + (kPv8 ? kLog2P8 : 0.f);
   const uint64_t c2 = pack2(c, c), bias2 = pack2(bias, bias);
 #pragma unroll
   for (int i = kBegin; i < kEnd; ++i) {
@@ -363,7 +380,7 @@ __device__ __forceinline__ void tile_row_exp(const uint32_t (&s)[kHN], uint32_t 
       if (2 * i + 1 >= n_valid) e1 = 0.f;
     }
     if (!(QMHA_KO & 2)) lsum[i & 1] = fadd2(lsum[i & 1], pack2(e0, e1));
-    p[i] = (QMHA_KO & 1) ? __float_as_uint(e0) : (kBf16 ? pack_bf16x2(e0, e1) : pack_f16x2(e0, e1));
+    p[i] = (QMHA_KO & 1) ? __float_as_uint(e0) : (kPv8 ? pack_u8x2(e0, e1) : (kBf16 ? pack_bf16x2(e0, e1) : pack_f16x2(e0, e1)));
   }
 }
 
@@ -402,12 +419,12 @@ __device__ __forceinline__ float tile_row_max_blk(uint32_t (&s)[kHN], float c0, 
   return fmaxf((float)max(lo0, lo1) * c0, (float)max(hi0, hi1) * c1);
 }
 
-template <bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2>
+template <bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2, bool kPv8 = false>
 __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint32_t (&p)[kHN / 2],
                                                  const StepConsts& k, float m_used, int n_valid,
                                                  uint64_t (&ls)[2], int one) {
-  const float b0 = QMHA_I2F == 5 ? k.lr0 - m_used : k.lr0 - fmaf(kMagicF, k.c0, m_used);
-  const float b1 = QMHA_I2F == 5 ? k.lr1 - m_used : k.lr1 - fmaf(kMagicF, k.c1, m_used);
+  const float b0 = (QMHA_I2F == 5 ? k.lr0 - m_used : k.lr0 - fmaf(kMagicF, k.c0, m_used)) + (kPv8 ? kLog2P8 : 0.f);
+  const float b1 = (QMHA_I2F == 5 ? k.lr1 - m_used : k.lr1 - fmaf(kMagicF, k.c1, m_used)) + (kPv8 ? kLog2P8 : 0.f);
   const uint64_t c2[2] = {pack2(k.c0, k.c0), pack2(k.c1, k.c1)};
   const uint64_t bias2[2] = {pack2(b0, b0), pack2(b1, b1)};
 #pragma unroll
@@ -429,16 +446,20 @@ __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint3
       if (2 * i + 1 >= n_valid) e1 = 0.f;
     }
     if (!(QMHA_KO & 2)) ls[g] = fadd2(ls[g], pack2(e0, e1));
-    p[i] = (QMHA_KO & 1) ? __float_as_uint(e0) : pack_f16x2(e0, e1);
+    p[i] = (QMHA_KO & 1) ? __float_as_uint(e0) : (kPv8 ? pack_u8x2(e0, e1) : pack_f16x2(e0, e1));
   }
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25, bool kBf16 = false>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25, bool kBf16 = false,
+          bool kPv8 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                 AttnParams prm) {
-  using C = Cfg<kInt8, kD>;
+  using C = Cfg<kInt8, kD, kPv8>;
+  // lazy rescale: the reference max is raised when a row max exceeds it by more than this many log2 units.  fp16 P
+  // holds 2^4 with full relative precision; 8-bit P codes are rn(127.5 p), so p must stay <= 2.
+  constexpr float kThr = kPv8 ? 1.0f : kRescaleThreshold;
   constexpr bool kSoftRing = QMHA_SOFT_RING == 2 || (QMHA_SOFT_RING == 1 && !kInt8);
   constexpr bool kLazyPv = QMHA_LAZY_PV == 2 || (QMHA_LAZY_PV == 1 && !kInt8);
   static_assert(!kBf16 || !kInt8, "bf16 is a variant of the 16-bit kernel");
@@ -550,7 +571,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (j >= C::kStagesV) mbar_wait(&bars->v_empty[st], (ph - 1) & 1, err_flag, 102, dead);
         mbar_arrive_expect_tx(&bars->v_full[st], C::kTileBytesV);
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub)
+        for (int sub = 0; sub < C::kSubTilesV; ++sub)
           tma_load_2d(sV + st * C::kTileBytesV + sub * C::kSubBytesV, &tm_v, &bars->v_full[st],
                       j * kBN + sub * 64, v_row);
       }
@@ -590,11 +611,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       auto issue_pv = [&](int t, int pbuf, int st, int half, bool accumulate) {
         const uint32_t d_tmem = tmem_base + (t ? kColO1 : kColO0);
         const uint32_t p_tmem = tmem_base + (t ? kColS1 : kColS0) + pbuf * kHN;
-        const uint64_t b0 = advance_smem_desc(v_desc0, (uint32_t)st * C::kTileBytesV + (uint32_t)half * C::kSubBytesV);
+        const uint64_t b0 = advance_smem_desc(v_desc0, (uint32_t)st * C::kTileBytesV + (uint32_t)half * C::kHalfOffV);
 #pragma unroll
         for (int ks = 0; ks < C::kStepsPV; ++ks) {
           const uint64_t b = advance_smem_desc(b0, (uint32_t)ks * 32);
-          if (do_mma) mma_f16_ts(d_tmem, p_tmem + ks * 8, b, kIdPV, (accumulate || ks > 0) ? 1u : 0u);
+          if (do_mma) {
+            if constexpr (kPv8) mma_i8_ts(d_tmem, p_tmem + ks * 8, b, C::kIdescPV8, (accumulate || ks > 0) ? 1u : 0u);
+            else mma_f16_ts(d_tmem, p_tmem + ks * 8, b, kIdPV, (accumulate || ks > 0) ? 1u : 0u);
+          }
         }
       };
 
@@ -625,7 +649,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (leader) {
           mbar_arrive_expect_tx(&bars->v_full[st], C::kTileBytesV);
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
+          for (int sub = 0; sub < C::kSubTilesV; ++sub)
             tma_load_2d(sV + st * C::kTileBytesV + sub * C::kSubBytesV, &tm_v, &bars->v_full[st],
                         j * kBN + sub * 64, unit * kD);
         }
@@ -795,8 +819,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int q = kB; q < kE; ++q) p[q] = sx[2 * q];
         return;
       }
-      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, kB, kE>(sx, p, k, m_used, kHN, ls, one);
-      else tile_row_exp<kInt8, false, kPolyEvery, kB, kE, kBf16>(sx, p, c, m_used, kHN, lsum, one);
+      if constexpr (kBlk) tile_row_exp_blk<false, kPolyEvery, kB, kE, kPv8>(sx, p, k, m_used, kHN, ls, one);
+      else tile_row_exp<kInt8, false, kPolyEvery, kB, kE, kBf16, kPv8>(sx, p, c, m_used, kHN, lsum, one);
     };
 
     // wait for S_t(i) and start its TMEM->register load (completion: tmem_wait_ld).  `probed` is the
@@ -831,8 +855,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     };
     // P_t(i) -> TMEM, over the score buffer of step i+1 (its scores are in registers by now),
     // then tell the MMA warp.
+    // fp16 / bf16 P: 32 columns; 8-bit P: the pairs' 16-bit halves are merged into 16 columns first
+    auto store_p = [&](uint32_t taddr, const uint32_t (&p)[kHN / 2]) {
+      if constexpr (kPv8) {
+        uint32_t q8[kHN / 4];
+#pragma unroll
+        for (int j = 0; j < kHN / 4; ++j) q8[j] = __byte_perm(p[2 * j], p[2 * j + 1], 0x5410);
+        tmem_st16(taddr, q8);
+      } else {
+        tmem_st32(taddr, &p[0]);
+      }
+    };
     auto publish = [&](int i, const uint32_t (&p)[kHN / 2]) {
-      tmem_st32(tP + ((i + 1) & 1) * kHN, &p[0]);
+      store_p(tP + ((i + 1) & 1) * kHN, p);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars->p_full[t][i & 1]);
@@ -842,7 +877,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // Called only when the warp voted for it: the old max is kept unless the new row max exceeds
     // it by more than 2^kRescaleThreshold.  P(i-1) must have been published before.
     auto raise_max = [&](int i, float mt) {
-      const bool need = mt > m_used + kRescaleThreshold;
+      const bool need = mt > m_used + kThr;
       const float m_new = need ? mt : m_used;
       if (i > 0) {
         const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
@@ -859,14 +894,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld32(tO + ch * 32, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
+          for (int q = 0; q < 32; ++q)   // INT8 P.V keeps O as int32: rescale through a float round trip (rare path)
+            o[q] = kPv8 ? (uint32_t)__float2int_rn((float)(int)o[q] * alpha) : __float_as_uint(__uint_as_float(o[q]) * alpha);
           tmem_st32(tO + ch * 32, o);
         }
         tmem_wait_st();
       }
       m_used = m_new;
     };
-    auto vote_raise = [&](float mt) { return __any_sync(0xffffffffu, mt > m_used + kRescaleThreshold) != 0; };
+    auto vote_raise = [&](float mt) { return __any_sync(0xffffffffu, mt > m_used + kThr) != 0; };
 
     // One pipelined step i < n_half-1 (always unmasked): exponentials of `cur` into `p`; publishes
     // `p_prev` = P(i-1) (if i > 0); if kPrefetch, fetches S(i+1) (unmasked, i.e. i+1 < n_half-1)
@@ -898,7 +934,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr int kA1 = kFa + 3, kA2 = kFa + 9;
       static_assert(kA2 < kFb && kFb < kHN / 2, "split points out of order");
       exps(Range<0, kFa>{}, cur, p, kc, ls);
-      if (!published) tmem_st32(tP + (i & 1) * kHN, &p_prev[0]);  // P(i-1) over the S(i) buffer
+      if (!published) store_p(tP + (i & 1) * kHN, p_prev);  // P(i-1) over the S(i) buffer
       exps(Range<kFa, kA1>{}, cur, p, kc, ls);
       if (!published) {
         tmem_wait_st();
@@ -940,12 +976,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (vote_raise(mt)) raise_max(i, mt);
       if constexpr (kBlk) {
         uint64_t ls[2] = {0ull, 0ull};
-        if (masked) tile_row_exp_blk<true, kPolyEvery>(cur, p, kl, m_used, n_valid, ls, one);
-        else tile_row_exp_blk<false, kPolyEvery>(cur, p, kl, m_used, kHN, ls, one);
+        if (masked) tile_row_exp_blk<true, kPolyEvery, 0, kHN / 2, kPv8>(cur, p, kl, m_used, n_valid, ls, one);
+        else tile_row_exp_blk<false, kPolyEvery, 0, kHN / 2, kPv8>(cur, p, kl, m_used, kHN, ls, one);
         fold_sums(ls, kl);
       } else {
-        if (masked) tile_row_exp<kInt8, true, kPolyEvery, 0, kHN / 2, kBf16>(cur, p, c, m_used, n_valid, lsum, one);
-        else tile_row_exp<kInt8, false, kPolyEvery, 0, kHN / 2, kBf16>(cur, p, c, m_used, kHN, lsum, one);
+        if (masked) tile_row_exp<kInt8, true, kPolyEvery, 0, kHN / 2, kBf16, kPv8>(cur, p, c, m_used, n_valid, lsum, one);
+        else tile_row_exp<kInt8, false, kPolyEvery, 0, kHN / 2, kBf16, kPv8>(cur, p, c, m_used, kHN, lsum, one);
       }
       if (tracer) tr[i * 4 + 2] = clock64();
       // P(i) goes over P(i-2).  In the steady state the fetch of S(i+1) proves that P·V(i-2) has
@@ -998,6 +1034,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (tracer && warp == 0) phase[3] = clock64();
     // ---------------------------------------------------------------- epilogue: O * sV / l
     // Everything that does not need O is computed before the wait (the divisions alone are ~300 clk).
+    auto of = [](uint32_t x) { return kPv8 ? (float)(int)x : __uint_as_float(x); };   // O: int32 with INT8 P.V
     float l, la, lb, lc, ld;
     unpack2(lsum[0], la, lb);
     unpack2(lsum[1], lc, ld);
@@ -1054,18 +1091,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (prm.out_dtype == 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 v = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
-                                         __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
+            const float4 v = make_float4(of(o[4 * j]) * inv, of(o[4 * j + 1]) * inv,
+                                         of(o[4 * j + 2]) * inv, of(o[4 * j + 3]) * inv);
             *reinterpret_cast<float4*>(buf + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
           }
         } else {   // 16-bit output: 32 rows x 64 B, SWIZZLE_64B (16-byte chunk index ^= (row >> 1) & 3)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 v;
-            v.x = pack16(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
-            v.y = pack16(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
-            v.z = pack16(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
-            v.w = pack16(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+            v.x = pack16(of(o[8 * j]) * inv, of(o[8 * j + 1]) * inv);
+            v.y = pack16(of(o[8 * j + 2]) * inv, of(o[8 * j + 3]) * inv);
+            v.z = pack16(of(o[8 * j + 4]) * inv, of(o[8 * j + 5]) * inv);
+            v.w = pack16(of(o[8 * j + 6]) * inv, of(o[8 * j + 7]) * inv);
             *reinterpret_cast<uint4*>(reinterpret_cast<char*>(buf) + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = v;
           }
         }
@@ -1095,8 +1132,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int ch = 0; ch < kChunks; ++ch) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 v = make_float4(__uint_as_float(o[ch][4 * j]) * inv, __uint_as_float(o[ch][4 * j + 1]) * inv,
-                                       __uint_as_float(o[ch][4 * j + 2]) * inv, __uint_as_float(o[ch][4 * j + 3]) * inv);
+          const float4 v = make_float4(of(o[ch][4 * j]) * inv, of(o[ch][4 * j + 1]) * inv,
+                                       of(o[ch][4 * j + 2]) * inv, of(o[ch][4 * j + 3]) * inv);
           *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
         }
         __syncwarp();
@@ -1123,13 +1160,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int i = 0; i < 32; i += 2) {
               const int col = ch * 32 + i;
               if (col < prm.d)
-                *reinterpret_cast<uint32_t*>(o16 + col) = pack16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+                *reinterpret_cast<uint32_t*>(o16 + col) = pack16(of(o[i]) * inv, of(o[i + 1]) * inv);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int col = ch * 32 + i;
-              if (col < prm.d) o16[col] = (uint16_t)(pack16(__uint_as_float(o[i]) * inv, 0.f) & 0xFFFFu);
+              if (col < prm.d) o16[col] = (uint16_t)(pack16(of(o[i]) * inv, 0.f) & 0xFFFFu);
             }
           }
         } else if (row_ok) {
@@ -1138,8 +1175,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int i = 0; i < 32; i += 4) {
               const int col = ch * 32 + i;
               if (col < prm.d) {
-                float4 v = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
-                                       __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                float4 v = make_float4(of(o[i]) * inv, of(o[i + 1]) * inv,
+                                       of(o[i + 2]) * inv, of(o[i + 3]) * inv);
                 *reinterpret_cast<float4*>(out + col) = v;
               }
             }
@@ -1147,7 +1184,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int col = ch * 32 + i;
-              if (col < prm.d) out[col] = __uint_as_float(o[i]) * inv;
+              if (col < prm.d) out[col] = of(o[i]) * inv;
             }
           }
         }
@@ -1237,14 +1274,15 @@ bool make_map_3d_out(CUtensorMap* m, const void* base, int out_dtype, uint64_t d
   return true;
 }
 
-template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25, bool kBf16 = false>
+template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25, bool kBf16 = false,
+          bool kPv8 = false>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
-  using C = Cfg<kInt8, kD>;
+  using C = Cfg<kInt8, kD, kPv8>;
   const uint64_t units = (uint64_t)a.B * a.H;
   CUtensorMap tq, tk, tv;
   if (!make_map_2d(&tq, a.Qp, C::kEltQK, units * a.n_pad, kD, kBM, C::kAtomQK / C::kEltQK, err) ||
       !make_map_2d(&tk, a.Kp, C::kEltQK, units * a.n_pad, kD, kBN, C::kAtomQK / C::kEltQK, err) ||
-      !make_map_2d(&tv, a.Vt, 2, units * kD, a.n_pad, kD, 64, err))
+      !make_map_2d(&tv, a.Vt, kPv8 ? 1 : 2, units * kD, a.n_pad, kD, kPv8 ? 128 : 64, err))
     return false;
   // output tensor map for the TMA-store epilogue (only when a 32-column chunk never straddles a head)
   CUtensorMap to;
@@ -1252,7 +1290,7 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   const bool tma_store = (a.d % 32) == 0 && getenv("QMHA_NO_TMA_STORE") == nullptr;
   if (tma_store && !make_map_3d_out(&to, a.O, a.out_dtype, (uint64_t)a.H * a.d, (uint64_t)a.N, (uint64_t)a.B, 32, 32, err))
     return false;
-  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb, kBf16>;
+  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb, kBf16, kPv8>;
   // block mode keeps one float4 of constants per 32-key block of the unit behind the barriers
   const size_t smem_bytes = (size_t)C::kSmemBytes + (kBlk ? (size_t)(a.n_pad / 32) * 16 : 0);
   if (smem_bytes > 227 * 1024) {
@@ -1306,6 +1344,7 @@ bool launch_attention(const AttnLaunch& a, std::string* err) {
   const bool blk = a.blk_scales != nullptr;
   if (blk && !a.int8) { *err = "block scales require the INT8 variant"; return false; }
   if (a.int8 && a.bf16) { *err = "bf16 selects the 16-bit kernel"; return false; }
+  if (a.pv8 && !a.int8) { *err = "INT8 P.V is a mode of the INT8 kernel"; return false; }
 #ifndef QMHA_ONLY_D128
   if (a.trace) {
     if (!(a.int8 && a.d_pad == 128)) { *err = "tracing is only built for the INT8 d=128 kernel"; return false; }
@@ -1315,6 +1354,8 @@ bool launch_attention(const AttnLaunch& a, std::string* err) {
 #if defined(QMHA_ONLY_D128)   // quick experiment builds (tools/build_variant.sh): d = 128, all-MUFU exponentials only
 #define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
   if (D == 128 && poly == 0) return launch_cfg<INT8, 128, 0, BLK, false, 6, 25, BF>(a, err);
+#define QMHA_DISPATCH_PV8(BLK, D)                                         \
+  if (D == 128 && poly == 0) return launch_cfg<true, 128, 0, BLK, false, 6, 25, false, true>(a, err);
 #elif defined(QMHA_BUILD_POLY)  // experiment builds with the FMA-pipe exp2 share (measured slower)
 #define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
   switch (poly) {                                                     \
@@ -1326,7 +1367,23 @@ bool launch_attention(const AttnLaunch& a, std::string* err) {
 #define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
   if (poly == 0) return launch_cfg<INT8, D, 0, BLK, false, 6, 25, BF>(a, err);
 #endif
-  if (a.int8 && blk) {
+#ifndef QMHA_DISPATCH_PV8
+#define QMHA_DISPATCH_PV8(BLK, D)                                         \
+  if (poly == 0) return launch_cfg<true, D, 0, BLK, false, 6, 25, false, true>(a, err);
+#endif
+  if (a.int8 && a.pv8 && blk) {
+    switch (a.d_pad) {
+      case 32: QMHA_DISPATCH_PV8(true, 32) break;
+      case 64: QMHA_DISPATCH_PV8(true, 64) break;
+      case 128: QMHA_DISPATCH_PV8(true, 128) break;
+    }
+  } else if (a.int8 && a.pv8) {
+    switch (a.d_pad) {
+      case 32: QMHA_DISPATCH_PV8(false, 32) break;
+      case 64: QMHA_DISPATCH_PV8(false, 64) break;
+      case 128: QMHA_DISPATCH_PV8(false, 128) break;
+    }
+  } else if (a.int8 && blk) {
     switch (a.d_pad) {
       case 32: QMHA_DISPATCH(true, true, 32, false) break;
       case 64: QMHA_DISPATCH(true, true, 64, false) break;
@@ -1352,6 +1409,7 @@ bool launch_attention(const AttnLaunch& a, std::string* err) {
     }
   }
 #undef QMHA_DISPATCH
+#undef QMHA_DISPATCH_PV8
   *err = "unsupported padded head dimension or kernel variant";
   return false;
 }

@@ -48,6 +48,7 @@ struct AttnLaunch {
   int B, N, H, d, n_pad, d_pad;
   bool int8;
   bool bf16 = false;    // 16-bit kernel with bf16 operands (Qp / Kp / Vt hold bf16)
+  bool pv8 = false;     // INT8 kernel with INT8 P.V: Vt holds int8 codes [units, d_pad, n_pad], P goes to the MMA as 8-bit codes
   cudaStream_t stream;
   bool units_y_limit_exceeded() const { return (long long)B * H > 65535; }
 };

@@ -220,7 +220,7 @@ prepare_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
                const TIn* __restrict__ V, const float* __restrict__ scales, void* __restrict__ Qp,
                void* __restrict__ Kp, uint16_t* __restrict__ Vt, int N, int H, int d, int n_pad,
                const float2* __restrict__ rope) {
-  constexpr bool kInt8 = kOut == 0;
+  constexpr bool kInt8 = kOut == 0 || kOut == 3;   // 3 = int8 codes with an int8 V^T (INT8 P.V mode)
   const int z = blockIdx.z, unit = blockIdx.y;
   const int b = unit / H, head = unit % H;
   const int n0 = blockIdx.x * kPrepRows;
@@ -274,6 +274,26 @@ prepare_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dst) + o) = pk;
       }
     }
+  } else if constexpr (kOut == 3) {
+    // V for the INT8 P.V mode: int8 codes, transposed (keys contiguous): Vt8[unit][dd][n]
+    constexpr int kStride8 = kD + 4;   // bytes
+    __shared__ __align__(4) int8_t tile8[kPrepRows * kStride8];
+    int8_t* Vt8 = reinterpret_cast<int8_t*>(Vt);
+    for (int r = rsub; r < kPrepRows; r += kRowsPerIter) {
+      float x[4];
+      load4(n0 + r, vec * 4, x);
+      const int q0 = quant1(x[0], inv_sc), q1 = quant1(x[1], inv_sc), q2 = quant1(x[2], inv_sc), q3 = quant1(x[3], inv_sc);
+      *reinterpret_cast<uint32_t*>(tile8 + r * kStride8 + vec * 4) =
+          (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+    }
+    __syncthreads();
+    constexpr int kQuads = kPrepRows / 4;   // threads per d-row: each emits 4 consecutive keys
+    const int kq = threadIdx.x % kQuads;
+    for (int dd = threadIdx.x / kQuads; dd < kD; dd += kPrepThreads / kQuads) {
+      const uint32_t o4 = (uint32_t)(uint8_t)tile8[(4 * kq + 0) * kStride8 + dd] | ((uint32_t)(uint8_t)tile8[(4 * kq + 1) * kStride8 + dd] << 8) |
+                          ((uint32_t)(uint8_t)tile8[(4 * kq + 2) * kStride8 + dd] << 16) | ((uint32_t)(uint8_t)tile8[(4 * kq + 3) * kStride8 + dd] << 24);
+      *reinterpret_cast<uint32_t*>(Vt8 + ((size_t)unit * kD + dd) * n_pad + n0 + 4 * kq) = o4;
+    }
   } else {
     // V: quantise/convert into a shared tile, then write it transposed (keys contiguous).
     constexpr int kStride = kD + 2;  // halves; odd word stride spreads the transposed reads
@@ -326,7 +346,7 @@ constexpr int kBlkRows = QMHA_BLKQ_ROWS;
 #ifndef QMHA_BLKQ_CTAS
 #define QMHA_BLKQ_CTAS 6
 #endif
-template <int kD, bool kRope, typename TIn>
+template <int kD, bool kRope, typename TIn, bool kV8 = false>
 __global__ void __launch_bounds__(kPrepThreads, kRope ? 3 : QMHA_BLKQ_CTAS)
 block_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
                       const TIn* __restrict__ V, float* __restrict__ scales,
@@ -402,6 +422,27 @@ block_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
                           ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
       *reinterpret_cast<uint32_t*>(dst + ((size_t)unit * n_pad + n) * kD + vec * 4) = pk;
     }
+  } else if constexpr (kV8) {
+    // INT8 P.V mode: V^T as int8 codes, Vt8[unit][dd][n]
+    constexpr int kStride8 = kD + 4;   // bytes
+    __shared__ __align__(4) int8_t tile8[kBlkRows * kStride8];
+    int8_t* Vt8 = reinterpret_cast<int8_t*>(Vt);
+#pragma unroll
+    for (int k = 0; k < kLoads; ++k) {
+      const int r = rsub + k * kRowsPerIter;
+      const float inv = inv_sc[k / kPerBlock];
+      const int q0 = quant1(x[k].x, inv), q1 = quant1(x[k].y, inv), q2 = quant1(x[k].z, inv), q3 = quant1(x[k].w, inv);
+      *reinterpret_cast<uint32_t*>(tile8 + r * kStride8 + vec * 4) =
+          (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+    }
+    __syncthreads();
+    constexpr int kQuads = kBlkRows / 4;
+    const int kq = threadIdx.x % kQuads;
+    for (int dd = threadIdx.x / kQuads; dd < kD; dd += kPrepThreads / kQuads) {
+      const uint32_t o4 = (uint32_t)(uint8_t)tile8[(4 * kq + 0) * kStride8 + dd] | ((uint32_t)(uint8_t)tile8[(4 * kq + 1) * kStride8 + dd] << 8) |
+                          ((uint32_t)(uint8_t)tile8[(4 * kq + 2) * kStride8 + dd] << 16) | ((uint32_t)(uint8_t)tile8[(4 * kq + 3) * kStride8 + dd] << 24);
+      *reinterpret_cast<uint32_t*>(Vt8 + ((size_t)unit * kD + dd) * n_pad + n0 + 4 * kq) = o4;
+    }
   } else {
     constexpr int kStride = kD + 2;
     __shared__ __half tile[kBlkRows * kStride];
@@ -428,7 +469,8 @@ template <int kD, typename TIn>
 cudaError_t launch_block_cfg(const PrepareArgs& a) {
   dim3 grid(a.n_pad / kBlkRows, a.B * a.H, 3);
   // the RoPE variant is a separate instantiation: the plain one stays inside its register budget
-  auto kern = a.rope ? block_quantize_kernel<kD, true, TIn> : block_quantize_kernel<kD, false, TIn>;
+  auto kern = a.v8 ? (a.rope ? block_quantize_kernel<kD, true, TIn, true> : block_quantize_kernel<kD, false, TIn, true>)
+                   : (a.rope ? block_quantize_kernel<kD, true, TIn> : block_quantize_kernel<kD, false, TIn>);
   kern<<<grid, kPrepThreads, 0, a.stream>>>(
       reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
       reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
@@ -926,7 +968,13 @@ cudaError_t launch_block_aux(const float* scales_v, float* aux, float* vmax, int
 }
 
 cudaError_t launch_prepare(const PrepareArgs& a) {
-  if (a.int8) {
+  if (a.int8 && a.v8) {
+    switch (a.d_pad) {
+      case 32: return launch_prepare_d<3, 32>(a);
+      case 64: return launch_prepare_d<3, 64>(a);
+      case 128: return launch_prepare_d<3, 128>(a);
+    }
+  } else if (a.int8) {
     switch (a.d_pad) {
       case 32: return launch_prepare_d<0, 32>(a);
       case 64: return launch_prepare_d<0, 64>(a);

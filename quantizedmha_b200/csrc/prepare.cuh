@@ -17,6 +17,7 @@ struct PrepareArgs {
   int B, N, H, d, n_pad, d_pad;
   bool int8;
   bool bf16 = false;  // 16-bit kernels: operands converted to bf16 instead of fp16
+  bool v8 = false;    // INT8 P.V mode: Vt receives int8 codes [B*H, d_pad, n_pad] instead of codes stored as fp16
   cudaStream_t stream;
   // fused RoPE (utils/verify.cu:9-23 applied to Q and K rows before absmax / quantisation):
   // table of {cos, sin}(pos * base^(-2k/d)) as float2 [N][d/2], built on the host; nullptr = off

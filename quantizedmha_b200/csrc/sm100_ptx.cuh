@@ -167,6 +167,15 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// INT8 P.V: A = unsigned 8-bit P read from TMEM (4 codes per 32-bit column), B = int8 V^T tile in shared memory.
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once every MMA issued so far by this thread has completed.
 // (Implies tcgen05.fence::before_thread_sync.)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -236,6 +245,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
       :
       : QMHA_IN8(v, 0), QMHA_IN8(v, 8), QMHA_IN8(v, 16), QMHA_IN8(v, 24), "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      :
+      : QMHA_IN8(v, 0), QMHA_IN8(v, 8), "r"(taddr)
       : "memory");
 }
 

@@ -10,15 +10,6 @@
 #include "../../quantizedmha_b200/csrc/sm100_ptx.cuh"
 using namespace qmha::ptx;
 
-__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 enum Pat {
   kI8ss64 = 0, kI8ss64acc, kI8ss128, kI8ss256, kF16ts128, kPvQk, kPvQk2tiles, kI8ts64, kI8ts128, kF16ss64x8,
   kF16ss128x8, kI8ss64x2tiles, kPvQk128, kF16ts128x8, kI8ss64one, kF16ts256, kCrossSeq, kCrossIl, kF16CrossSeq, kF16CrossIl, kF16SameSeq, kNumPat
