@@ -290,6 +290,10 @@ class Job:
                 "tolerance": {"max_abs": tol_abs, "rel_l2": tol_rel}}
 
 
+def flops_of(B, H, N, d):
+    return 4.0 * B * H * N * N * d
+
+
 def copy_roof_ms(torch, dev, bufs_in, buf_out, reps=2):
     """Raw platform roof of the e2e arm: the same pinned buffers moved by one cudaMemcpyAsync each, all host->device
     copies on one stream and the device->host copy on another (full duplex), nothing else running."""
@@ -425,6 +429,18 @@ def run_native(args):
         signed = {"attn_ms": s_attn, "attn_tflops_per_gpu": 4.0 * Bl * H * N * N * d / (s_attn / 1e3) / 1e12,
                   "data": "0.5*N(0,1) (tests/generate_golden.cpp:123-138 distribution)", "parity": s_par}
 
+    # ---- the opt-in INT8 P.V mode (P as 8-bit codes on the INT8 pipe: the reference's P semantics) on the same inputs
+    pv8 = None
+    if kernel == "int8" and not args.no_pv8:
+        j8 = Job(torch, qm, dev, Bl, H, N, d, "int8_pv8", gran, 42 + rank)
+        p_ms, p_attn, p_prep, _ = j8.time(min(K, 5), 2, barrier)
+        p_par = j8.parity() if rank == 0 else None
+        p_ms, p_attn, p_prep = max_over_ranks([p_ms, p_attn, p_prep])
+        pv8 = {"kernel": "int8_pv8 (QMHA_KERNEL_INT8_PV8): s8*s8->s32 (Q.K^T), u8*s8->s32 (P.V)", "ms_per_step": p_ms, "attn_ms": p_attn,
+               "prep_ms": p_prep, "tflops": flops_of(Bl, H, N, d) * (world if scaling == "weak" else 1) / (p_ms / 1e3) / 1e12,
+               "attn_tflops_per_gpu": flops_of(Bl, H, N, d) / (p_attn / 1e3) / 1e12, "parity": p_par}
+        del j8
+
     # ---- BASELINE config 5 (B=32, H=32, N=16384, d=128), units split over the ranks: strong scaling
     scaling_c5 = None
     if world > 1 and args.workload == "c4" and not args.no_c5:
@@ -535,6 +551,7 @@ def run_native(args):
                 "fp16_buffers": (dict(e2e16, value=flops_all / (e2e16["ms_per_step"] / 1e3) / 1e12, unit="TFLOP/s") if e2e16 else None)},
         "parity": parity,
         "signed_inputs": signed,
+        "int8_pv_mode": pv8,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -566,6 +583,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = all host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-signed", action="store_true", help="skip the extra timing on signed inputs")
+    ap.add_argument("--no-pv8", action="store_true", help="skip the extra timing of the opt-in INT8 P.V mode")
     ap.add_argument("--no-e2e16", action="store_true", help="skip the fp16-host-buffer variant of the e2e measurement")
     ap.add_argument("--no-c5", action="store_true", help="N>1: skip the C5 strong-scaling measurement")
     ap.add_argument("--scales", default="block", choices=["head", "block", "tensor"],

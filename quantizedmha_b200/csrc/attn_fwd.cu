@@ -62,14 +62,27 @@ constexpr int kMmaSplit = QMHA_MMA_SPLIT;
 //   QMHA_LAZY_PV: "P.V(i) retired" is read off s_full(i+3); only the last three half-steps keep a pv_done commit.
 // Same-box A/B at the headline shape (clocks per CTA): FP16 219.6 k -> 198.3 k with both (-10 %: that kernel waits
 // on the tensor side); INT8 184.6 k -> 193.1 k with both (+4.5 %: the softmax warps set the pace there and pay for
-// the extra arrive), so INT8 keeps committing the ring barriers.
+// the extra arrive), so INT8 keeps committing the ring barriers.  QMHA_LAZY_PV alone is neutral to -1 % for INT8 (184.5 k
+// against 186.4 k with the bias MMA in place) and is on for every kernel.
 #ifndef QMHA_SOFT_RING
 #define QMHA_SOFT_RING 1
 #endif
 #ifndef QMHA_LAZY_PV
-#define QMHA_LAZY_PV 1
+#define QMHA_LAZY_PV 2
 #endif
 static_assert((QMHA_SOFT_RING == 0 && QMHA_LAZY_PV == 0) || kMmaSplit == 2, "written for the two-warp MMA issue");
+// QMHA_BIAS_MMA (INT8 kernels): the tensor pipe delivers the scores as FLOAT BIT PATTERNS.  One extra kind::f16
+// instruction per score tile writes the constant 12582912.0f = 0x4B400000 into the accumulator (A = 128x16 tile of 768.0,
+// B = 64x16 tile of 1024.0: 16 * 768 * 1024 = 1.5 * 2^23 exactly; every element equal, so the swizzle does not matter) and
+// the four kind::i8 instructions ACCUMULATE their int32 dot products onto that bit pattern: bits(S) = 0x4B400000 + s is the
+// float 12582912 + s, which the exponent FMA consumes as it is.  The per-element integer add of the int->float trick — the one
+// instruction whose removal moved the kernel in the knock-out runs (5.85 -> 5.28 ms) — disappears from the softmax warps; the
+// tensor side pays one more feed-bound instruction (~48 clk) per tile and half-step.
+#ifndef QMHA_BIAS_MMA
+#define QMHA_BIAS_MMA 1
+#endif
+constexpr bool kBiasMma = QMHA_BIAS_MMA != 0;
+constexpr int kBiasTileBytes = 4096 + 2048;   // A: 128 rows x 32 B, B: 64 rows x 32 B (fp16, SWIZZLE_32B layout)
 constexpr int kAllocWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr int kTmaWarpV = 10;
@@ -114,7 +127,10 @@ struct Cfg {
   static constexpr int kStagesK = kStagesV + 1;
 #endif
   static_assert(kStagesV >= 2, "need at least double buffering");
-  static constexpr int kSmemTiles = 2 * kTileBytesQK + kStagesK * kTileBytesQK + kStagesV * kTileBytesV;
+  static constexpr bool kBias = kInt8 && kBiasMma;
+  static constexpr int kSmemTiles = 2 * kTileBytesQK + kStagesK * kTileBytesQK + kStagesV * kTileBytesV +
+                                    (kBias ? kBiasTileBytes : 0);
+  static constexpr uint32_t kIdescBias = make_idesc(kAccF32, kFmtF16, kFmtF16, kBM, kHN);
   static constexpr int kSmemBytes = kSmemTiles + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr uint32_t kIdescQK =
       kInt8 ? make_idesc(kAccS32, kFmtS8, kFmtS8, kBM, kHN)
@@ -193,7 +209,7 @@ __device__ __forceinline__ float tile_row_max(uint32_t (&s)[kHN], float c, int n
     if constexpr (kMasked) {
 #pragma unroll
       for (int i = 0; i < kHN; ++i)
-        if (i >= n_valid) s[i] = (uint32_t)(-(1 << 22));
+        if (i >= n_valid) s[i] = (uint32_t)((kBiasMma ? kMagicI2F : 0) - (1 << 22));
     }
     int m0 = max((int)s[0], (int)s[1]), m1 = max((int)s[2], (int)s[3]);
     int m2 = max((int)s[4], (int)s[5]), m3 = max((int)s[6], (int)s[7]);
@@ -204,7 +220,7 @@ __device__ __forceinline__ float tile_row_max(uint32_t (&s)[kHN], float c, int n
       m2 = max(max(m2, (int)s[i + 4]), (int)s[i + 5]);
       m3 = max(max(m3, (int)s[i + 6]), (int)s[i + 7]);
     }
-    return (float)max(max(m0, m1), max(m2, m3)) * c;
+    return (float)(max(max(m0, m1), max(m2, m3)) - (kBiasMma ? kMagicI2F : 0)) * c;   // (biased scores stay monotone)
   } else {
     if constexpr (kMasked) {
 #pragma unroll
@@ -289,6 +305,7 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& e0, fl
 #define QMHA_I2F 0
 #endif
 __device__ __forceinline__ float i2f_magic(uint32_t s, int one, int idx) {
+  if (kBiasMma) return __uint_as_float(s);           // the tensor pipe already delivered 0x4B400000 + s
   if (QMHA_I2F == 3) return __uint_as_float(s);   // timing experiment only: no conversion at all (wrong results)
   if (QMHA_I2F == 5) return __int2float_rn((int)s);   // I2FP: a real conversion, no magic bias in the FMA
   if (QMHA_I2F == 1 || (QMHA_I2F == 2 && (idx & 1))) {
@@ -323,6 +340,7 @@ __device__ __forceinline__ uint32_t pace_token(const uint32_t (&p)[kHN / 2], int
 }
 __device__ __forceinline__ void i2f_pair(uint32_t s0, uint32_t s1, int one, int i, float& f0, float& f1,
                                          uint32_t tok = 0u) {
+  if (kBiasMma) { f0 = __uint_as_float(s0); f1 = __uint_as_float(s1); return; }
   if (QMHA_I2F == 4) {  // timing experiment only: one 64-bit add per pair (the carry makes s1 off by one when s0 < 0)
     uint64_t v;
     asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(s0), "r"(s1));
@@ -402,7 +420,7 @@ __device__ __forceinline__ float tile_row_max_blk(uint32_t (&s)[kHN], float c0, 
   if constexpr (kMasked) {
 #pragma unroll
     for (int i = 0; i < kHN; ++i)
-      if (i >= n_valid) s[i] = (uint32_t)(-(1 << 22));
+      if (i >= n_valid) s[i] = (uint32_t)((kBiasMma ? kMagicI2F : 0) - (1 << 22));
   }
   int lo0 = max((int)s[0], (int)s[1]), lo1 = max((int)s[2], (int)s[3]);
   int hi0 = max((int)s[32], (int)s[33]), hi1 = max((int)s[34], (int)s[35]);
@@ -415,8 +433,9 @@ __device__ __forceinline__ float tile_row_max_blk(uint32_t (&s)[kHN], float c0, 
   }
   // A block that holds no real key contributes nothing: its scale is the quantiser's 1e-8 floor, so a
   // scaled sentinel would read as ~0 and could lift the row max above every real (negative) logit.
-  if (kMasked && n_valid <= kHN / 2) return (float)max(lo0, lo1) * c0;
-  return fmaxf((float)max(lo0, lo1) * c0, (float)max(hi0, hi1) * c1);
+  constexpr int kOff = kBiasMma ? kMagicI2F : 0;
+  if (kMasked && n_valid <= kHN / 2) return (float)(max(lo0, lo1) - kOff) * c0;
+  return fmaxf((float)(max(lo0, lo1) - kOff) * c0, (float)(max(hi0, hi1) - kOff) * c1);
 }
 
 template <bool kMasked, int kPolyEvery, int kBegin = 0, int kEnd = kHN / 2, bool kPv8 = false>
@@ -472,7 +491,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 2 * C::kTileBytesQK;
   uint8_t* sV = sK + C::kStagesK * C::kTileBytesQK;
-  Barriers* bars = reinterpret_cast<Barriers*>(sV + C::kStagesV * C::kTileBytesV);
+  uint8_t* sBias = sV + C::kStagesV * C::kTileBytesV;   // constant operand tiles of the bias MMA (INT8 kernels)
+  Barriers* bars = reinterpret_cast<Barriers*>(sBias + (C::kBias ? kBiasTileBytes : 0));
   float4* blk_tab = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 512);  // block mode only
 
   const int warp = threadIdx.x >> 5;
@@ -533,6 +553,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
   }
+  if constexpr (C::kBias) {   // 384 threads x 16 B = 6 KB: A tile all 768.0 (0x6200), B tile all 1024.0 (0x6400)
+    const uint32_t w = threadIdx.x < 256 ? 0x62006200u : 0x64006400u;
+    reinterpret_cast<uint4*>(sBias)[threadIdx.x] = make_uint4(w, w, w, w);
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor pipe's (async proxy) operand reads
+  }
   if (warp == kAllocWarp) {
     tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
@@ -586,6 +611,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const bool leader = elect_one() != 0;
       const bool do_mma = leader && !prm.debug_no_mma;
       // Base descriptors are built once; per MMA only the 14-bit address field moves (one add).
+      const uint64_t bias_a = make_smem_desc(smem_u32(sBias), 32), bias_b = make_smem_desc(smem_u32(sBias) + 4096, 32);
       const uint64_t q_desc0 = make_smem_desc(sQ_a, C::kAtomQK);
       const uint64_t k_desc0 = make_smem_desc(sK_a, C::kAtomQK);
       const uint64_t v_desc0 = make_smem_desc(sV_a, 128);
@@ -594,6 +620,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t d_tmem = tmem_base + (t ? kColS1 : kColS0) + buf * kHN;
         const uint64_t a0 = advance_smem_desc(q_desc0, (uint32_t)t * C::kTileBytesQK);
         const uint64_t b0 = advance_smem_desc(k_desc0, (uint32_t)st * C::kTileBytesQK + (uint32_t)half * C::kHalfBytesQK);
+        if constexpr (C::kBias) {   // accumulator := 0x4B400000 everywhere; the int8 dot products accumulate onto it
+          if (do_mma) mma_f16_ss(d_tmem, bias_a, bias_b, C::kIdescBias, 0u);
+        }
 #pragma unroll
         for (int ks = 0; ks < C::kStepsQK; ++ks) {
           constexpr int kDummy = 0; (void)kDummy;
@@ -602,7 +631,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint64_t a = advance_smem_desc(a0, off);
           const uint64_t b = advance_smem_desc(b0, off);
           if (do_mma) {
-            if constexpr (kInt8) mma_i8_ss(d_tmem, a, b, kIdQK, ks > 0);
+            if constexpr (kInt8) mma_i8_ss(d_tmem, a, b, kIdQK, (C::kBias || ks > 0) ? 1u : 0u);
             else mma_f16_ss(d_tmem, a, b, kIdQK, ks > 0);
           }
         }
@@ -993,7 +1022,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint32_t sA[kHN], sB[kHN], pA[kHN / 2], pB[kHN / 2];
     if (prm.debug_no_mma) {
 #pragma unroll
-      for (int q = 0; q < kHN; ++q) sA[q] = (uint32_t)((int)((threadIdx.x * 37 + q * 101) % 4001) - 2000);
+      for (int q = 0; q < kHN; ++q) sA[q] = (uint32_t)((int)((threadIdx.x * 37 + q * 101) % 4001) - 2000 + (C::kBias ? kMagicI2F : 0));
       tmem_st32(tS, &sA[0]); tmem_st32(tS + 32, &sA[32]); tmem_st32(tS + 64, &sA[0]); tmem_st32(tS + 96, &sA[32]);
       tmem_wait_st();
     }
@@ -1337,6 +1366,14 @@ int attention_max_block_keys(int d_pad) {
   return (227 * 1024 - tiles) / 16 * 32;
 }
 
+// split points of the softmax step (in exp2 pairs): P store after QMHA_FA pairs, row max of the next scores after QMHA_FB
+#ifndef QMHA_FA
+#define QMHA_FA 6
+#endif
+#ifndef QMHA_FB
+#define QMHA_FB 25
+#endif
+
 bool launch_attention(const AttnLaunch& a, std::string* err) {
   if (a.units_y_limit_exceeded()) { *err = "B*h exceeds the CUDA grid.y limit (65535)"; return false; }
   // a.variant = k: exp2 of every k-th score pair goes to the FMA-pipe polynomial (0 = all MUFU)
@@ -1353,23 +1390,23 @@ bool launch_attention(const AttnLaunch& a, std::string* err) {
 #endif
 #if defined(QMHA_ONLY_D128)   // quick experiment builds (tools/build_variant.sh): d = 128, all-MUFU exponentials only
 #define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
-  if (D == 128 && poly == 0) return launch_cfg<INT8, 128, 0, BLK, false, 6, 25, BF>(a, err);
+  if (D == 128 && poly == 0) return launch_cfg<INT8, 128, 0, BLK, false, QMHA_FA, QMHA_FB, BF>(a, err);
 #define QMHA_DISPATCH_PV8(BLK, D)                                         \
-  if (D == 128 && poly == 0) return launch_cfg<true, 128, 0, BLK, false, 6, 25, false, true>(a, err);
+  if (D == 128 && poly == 0) return launch_cfg<true, 128, 0, BLK, false, QMHA_FA, QMHA_FB, false, true>(a, err);
 #elif defined(QMHA_BUILD_POLY)  // experiment builds with the FMA-pipe exp2 share (measured slower)
 #define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
   switch (poly) {                                                     \
-    case 0: return launch_cfg<INT8, D, 0, BLK, false, 6, 25, BF>(a, err);        \
-    case 4: return launch_cfg<INT8, D, 4, BLK, false, 6, 25, BF>(a, err);        \
-    case 8: return launch_cfg<INT8, D, 8, BLK, false, 6, 25, BF>(a, err);        \
+    case 0: return launch_cfg<INT8, D, 0, BLK, false, QMHA_FA, QMHA_FB, BF>(a, err);        \
+    case 4: return launch_cfg<INT8, D, 4, BLK, false, QMHA_FA, QMHA_FB, BF>(a, err);        \
+    case 8: return launch_cfg<INT8, D, 8, BLK, false, QMHA_FA, QMHA_FB, BF>(a, err);        \
   }
 #else
 #define QMHA_DISPATCH(INT8, BLK, D, BF)                                   \
-  if (poly == 0) return launch_cfg<INT8, D, 0, BLK, false, 6, 25, BF>(a, err);
+  if (poly == 0) return launch_cfg<INT8, D, 0, BLK, false, QMHA_FA, QMHA_FB, BF>(a, err);
 #endif
 #ifndef QMHA_DISPATCH_PV8
 #define QMHA_DISPATCH_PV8(BLK, D)                                         \
-  if (poly == 0) return launch_cfg<true, D, 0, BLK, false, 6, 25, false, true>(a, err);
+  if (poly == 0) return launch_cfg<true, D, 0, BLK, false, QMHA_FA, QMHA_FB, false, true>(a, err);
 #endif
   if (a.int8 && a.pv8 && blk) {
     switch (a.d_pad) {

@@ -259,7 +259,7 @@ def test_host_buffer_entry_pipelines_over_head_groups(qm, torch, oracle, kern, g
 def test_solve_falls_back_to_per_head_scales_when_the_block_table_no_longer_fits(qm, torch, oracle):
     L = qm.lib()
     assert L.qmha_granularity_for(8192, 4096, 32) == qm.GRAN_BLOCK
-    assert L.qmha_granularity_for(65536, 128, 1) == qm.GRAN_BLOCK
+    assert L.qmha_granularity_for(49152, 128, 1) == qm.GRAN_BLOCK
     assert L.qmha_granularity_for(70000, 128, 1) == qm.GRAN_HEAD
     assert L.qmha_granularity_for(300000, 64, 2) == qm.GRAN_BLOCK     # d = 32: small tiles leave room for a longer table
     assert L.qmha_granularity_for(1000000, 64, 2) == qm.GRAN_HEAD

@@ -64,7 +64,7 @@ def test_extended_entry_host_logic(qm):
     # block scales while the per-block table of one unit fits in shared memory behind the tiles, per-head beyond
     assert L.qmha_granularity_for(8192, 4096, 32) == qm.GRAN_BLOCK
     assert L.qmha_granularity_for(16384, 4096, 32) == qm.GRAN_BLOCK
-    assert L.qmha_granularity_for(68608, 128, 1) == qm.GRAN_BLOCK and L.qmha_granularity_for(68609, 128, 1) == qm.GRAN_HEAD
+    assert L.qmha_granularity_for(56320, 128, 1) == qm.GRAN_BLOCK and L.qmha_granularity_for(56321, 128, 1) == qm.GRAN_HEAD
     assert L.qmha_granularity_for(512, 30, 2) == qm.GRAN_HEAD          # d = 15: scalar two-pass path
     assert L.qmha_default_granularity(4096, 32) == qm.GRAN_BLOCK
 
