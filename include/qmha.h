@@ -182,6 +182,9 @@ int qmha_debug_attention_trace(const void* Qp, const void* Kp, const uint16_t* V
 /* Development aid: with QMHA_CYCLES=1 in the environment, every qmha_attention_prepared() launch adds
  * the SM clocks each CTA was resident to a device counter; out2 = {sum of clocks, CTAs}. */
 int qmha_debug_cycles(unsigned long long* out2, int reset);
+/* Per SM s < n_sms (<= 192): out[2*s] = SM clocks between the first CTA start and the last CTA end on that SM since
+ * the last reset (one launch between resets), out[2*s+1] = 0. */
+int qmha_debug_sm_spans(unsigned long long* out, int n_sms, int reset);
 
 /* ---- fused RoPE ------------------------------------------------------------
  * The reference's CPU check rotates Q and K (utils/verify.cu:56-69) but no GPU kernel ever calls

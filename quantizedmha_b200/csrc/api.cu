@@ -163,8 +163,8 @@ int get_workspace(int dev, size_t qk_bytes, size_t vt_bytes, size_t scale_elems,
     }
   }
   if (!w.cycles && getenv("QMHA_CYCLES")) {
-    if ((e = cudaMalloc(&w.cycles, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
-    cudaMemset(w.cycles, 0, 2 * sizeof(unsigned long long));
+    if ((e = cudaMalloc(&w.cycles, qmha::kCycleWords * sizeof(unsigned long long))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
+    cudaMemset(w.cycles, 0, qmha::kCycleWords * sizeof(unsigned long long));
   }
   if (qk_bytes > w.qk_bytes) {
     cudaDeviceSynchronize();
@@ -696,7 +696,30 @@ int qmha_debug_cycles(unsigned long long* out2, int reset) {
   if (!w->cycles) return fail("set QMHA_CYCLES=1 before the first call");
   cudaError_t e = cudaMemcpy(out2, w->cycles, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return fail_cuda("reading the cycle counters", e);
-  if (reset) cudaMemset(w->cycles, 0, 2 * sizeof(unsigned long long));
+  if (reset) cudaMemset(w->cycles, 0, qmha::kCycleWords * sizeof(unsigned long long));
+  g_err.clear();
+  return 0;
+}
+
+// Same counters per SM: out[2*s] = clocks between the first CTA start and the last CTA end on SM s since the last
+// reset (0 if the SM ran nothing), out[2*s+1] unused; n_sms <= 192.  Meaningful for ONE launch between resets.
+int qmha_debug_sm_spans(unsigned long long* out, int n_sms, int reset) {
+  const int dev = require_device();
+  if (dev < 0) return 1;
+  Workspace* w;
+  std::unique_lock<std::mutex> call_lock;
+  if (get_workspace(dev, 0, 0, 0, &w, &call_lock)) return 1;
+  if (!w->cycles) return fail("set QMHA_CYCLES=1 before the first call");
+  if (n_sms < 0 || n_sms > qmha::kCycleSms) return fail("n_sms out of range");
+  std::vector<unsigned long long> h(qmha::kCycleWords);
+  cudaError_t e = cudaMemcpy(h.data(), w->cycles, qmha::kCycleWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return fail_cuda("reading the cycle counters", e);
+  for (int s = 0; s < n_sms; ++s) {
+    const unsigned long long ns = h[2 + 2 * s], en = h[3 + 2 * s];
+    out[2 * s] = en ? en - ~ns : 0ull;
+    out[2 * s + 1] = 0ull;
+  }
+  if (reset) cudaMemset(w->cycles, 0, qmha::kCycleWords * sizeof(unsigned long long));
   g_err.clear();
   return 0;
 }

@@ -579,6 +579,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int st = j % C::kStagesK;
         const uint32_t ph = (uint32_t)(j / C::kStagesK);
         if (j >= C::kStagesK) mbar_wait(&bars->k_empty[st], (ph - 1) & 1, err_flag, 101, dead);
+        if (QMHA_KO & 32) { mbar_arrive(&bars->k_full[st]); continue; }   // timing experiment: no K traffic after the first ring fill
         mbar_arrive_expect_tx(&bars->k_full[st], C::kTileBytesQK);
 #pragma unroll
         for (int sub = 0; sub < C::kSubQK; ++sub)
@@ -594,6 +595,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int st = j % C::kStagesV;
         const uint32_t ph = (uint32_t)(j / C::kStagesV);
         if (j >= C::kStagesV) mbar_wait(&bars->v_empty[st], (ph - 1) & 1, err_flag, 102, dead);
+        if ((QMHA_KO & 32) && j >= C::kStagesV) { mbar_arrive(&bars->v_full[st]); continue; }   // same for V^T
         mbar_arrive_expect_tx(&bars->v_full[st], C::kTileBytesV);
 #pragma unroll
         for (int sub = 0; sub < C::kSubTilesV; ++sub)
@@ -1231,8 +1233,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tmem_dealloc(tmem_base, kTmemCols);
   }
   if (prm.cycles != nullptr && threadIdx.x == 0) {   // development aid: SM clocks this CTA was resident
-    atomicAdd(prm.cycles, (unsigned long long)(clock64() - t_entry));
+    const long long t_exit = clock64();
+    atomicAdd(prm.cycles, (unsigned long long)(t_exit - t_entry));
     atomicAdd(prm.cycles + 1, 1ull);
+    // per SM: {~(earliest CTA start), latest CTA end} -> span of the launch on that SM against the sum of residencies
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid < (uint32_t)kCycleSms) {
+      atomicMax(prm.cycles + 2 + 2 * smid, ~(unsigned long long)t_entry);
+      atomicMax(prm.cycles + 3 + 2 * smid, (unsigned long long)t_exit);
+    }
   }
 }
 

@@ -6,6 +6,9 @@
 
 namespace qmha {
 
+constexpr int kCycleSms = 192;                     // per-SM slots of the development cycle counters
+constexpr int kCycleWords = 2 + 2 * kCycleSms;     // {sum, CTAs, per SM: ~earliest start, latest end}
+
 struct AttnParams {
   void* O;              // [B, N, H*d] fp32 / fp16 / bf16 (out_dtype)
   const float* scales;  // [3, units] (INT8 variant) or nullptr

@@ -137,6 +137,18 @@ for rnd in range(args.rounds):
                    "max_abs_vs_f16": float((out - anchor).abs().max().item())}
             if has_cyc and L.qmha_debug_cycles(cyc, 1) == 0 and cyc[1]:
                 rec["cta_kclk"] = cyc[0] / cyc[1] / 1e3     # mean residency of a CTA, exact SM clocks
+            if has_cyc and hasattr(L, "qmha_debug_sm_spans"):   # one launch: per-SM span against the sum of CTA residencies
+                L.qmha_debug_sm_spans.argtypes = [C.POINTER(C.c_ulonglong), C.c_int, C.c_int]
+                sp = (C.c_ulonglong * 384)()
+                L.qmha_debug_cycles(cyc, 1)
+                launch(L)
+                torch.cuda.synchronize()
+                if L.qmha_debug_cycles(cyc, 0) == 0 and L.qmha_debug_sm_spans(sp, 192, 1) == 0:
+                    spans = [sp[2 * i] for i in range(192) if sp[2 * i]]
+                    rec["one_launch"] = {"sms": len(spans), "ctas": cyc[1], "resid_sum_mclk": cyc[0] / 1e6,
+                                         "span_sum_mclk": sum(spans) / 1e6, "span_max_kclk": max(spans) / 1e3,
+                                         "span_mean_kclk": sum(spans) / len(spans) / 1e3,
+                                         "gap_frac_of_span": 1.0 - cyc[0] / sum(spans)}
             rec.update(clocks_between(w0 + 0.03, w1))
             if rec.get("sm_mhz"):
                 rec["mclk"] = ms * 1e-3 * rec["sm_mhz"]
