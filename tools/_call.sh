@@ -1,3 +1,8 @@
-n=8
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_n$n.log 2> gpurun_out/scale_n$n.err
-tail -1 gpurun_out/scale_n$n.log | cut -c1-300
+# compute-sanitizer memcheck over the shipped kernels on small shapes (ragged N, every head dim, every kernel)
+O=gpurun_out/sanitize.txt; : > $O
+for args in "--kernel=fa_tc_int8_b --N=300 --d_model=256 --h=2" "--kernel=fa_tc_int8_b --N=520 --d_model=128 --h=2 --random" "--kernel=fa_tc_int8_b --N=257 --d_model=64 --h=2 --random --rope" "--kernel=fa_tc_v2a --N=300 --d_model=256 --h=2 --random" "--kernel=fa_b200_bf16 --N=130 --d_model=128 --h=2 --random" "--kernel=int8_pv8 --N=300 --d_model=256 --h=2 --random"; do
+  echo "== compute-sanitizer --tool memcheck bin/profile_fa_tc_int8_b $args --warmup=0 --runs=1" >> $O
+  timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 bin/profile_fa_tc_int8_b $args --warmup=0 --runs=1 2>&1 | grep -v "^=========\s*$" | tail -6 >> $O
+  echo "exit ${PIPESTATUS[0]}" >> $O
+done
+cat $O
