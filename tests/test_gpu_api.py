@@ -10,6 +10,7 @@ rounded to 2^-9 relative) and at 2e-3 against the oracle evaluated on the bf16-r
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -385,3 +386,32 @@ def test_persistent_per_head_quantiser_is_bit_identical(qm, torch, oracle, shape
     monkeypatch.delenv("QMHA_STREAM_QUANT", raising=False)
     assert np.array_equal(_unpack_rows(Kp, B, N, h, d), codes) and np.array_equal(sc[1].cpu().numpy(), s)
     assert (Qp[:, N:, :] == 0).all() and (Vt[:, :, N:] == 0).all()
+
+
+@pytest.mark.gpu
+def test_development_cycle_counters_account_for_every_cta(tmp_path):
+    """qmha_debug_cycles / qmha_debug_sm_spans (QMHA_CYCLES=1, set before the first call, hence a fresh process; counted for
+    qmha_attention_prepared launches): one launch
+    of 2 x 4 units x 2 query blocks reports 16 CTAs, a positive residency sum, and per-SM spans that cover it."""
+    script = tmp_path / "cycles.py"
+    script.write_text(
+        "import ctypes as C, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import torch, quantizedmha_b200 as qm\n"
+        "L = qm.lib()\n"
+        "L.qmha_debug_sm_spans.argtypes = [C.POINTER(C.c_ulonglong), C.c_int, C.c_int]\n"
+        "q, k, v = (torch.rand((2, 512, 512), device='cuda') for _ in range(3))\n"
+        "Qp, Kp, Vt, sc = qm.quantize_qkv(q, k, v, 4, qm.GRAN_BLOCK); out = torch.empty_like(q)\n"
+        "P = lambda t: C.c_void_p(t.data_ptr())\n"
+        "run = lambda: L.qmha_attention_prepared(P(Qp), P(Kp), P(Vt), P(sc), P(out), 2, 512, 512, 4, qm.binding.KERNEL_INT8, qm.GRAN_BLOCK, None)\n"
+        "assert run() == 0; torch.cuda.synchronize()\n"
+        "c = (C.c_ulonglong * 2)(); assert L.qmha_debug_cycles(c, 1) == 0\n"
+        "assert run() == 0; torch.cuda.synchronize()\n"
+        "assert L.qmha_debug_cycles(c, 0) == 0\n"
+        "sp = (C.c_ulonglong * 384)(); assert L.qmha_debug_sm_spans(sp, 192, 1) == 0\n"
+        "spans = [sp[2 * i] for i in range(192) if sp[2 * i]]\n"
+        "print(c[1], c[0], len(spans), sum(spans))\n"
+        "assert c[1] == 16 and c[0] > 0 and 1 <= len(spans) <= 16 and sum(spans) >= c[0] * 0.99\n"
+        "assert L.qmha_debug_sm_spans(sp, 193, 0) != 0\n")
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, QMHA_CYCLES="1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
