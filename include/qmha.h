@@ -90,7 +90,18 @@ typedef struct qmha_args {
   float rope_base;          /* used when rope == 1; <= 1 means 10000                                     */
   int variant;              /* -1 (tuning aid: exp2 share on the FMA pipe, only in QMHA_BUILD_POLY builds)*/
   void* stream;             /* cudaStream_t; NULL = legacy default stream                                */
+  /* Output placement (the caller-side concat / gather folded into the kernel's epilogue).
+   * O may be a (batch, head-range) SLAB of a larger tensor: o_row_stride / o_batch_stride are the distances, in
+   * elements of out_dtype, between consecutive rows / batch entries of O (0 = dense: d_model and N * d_model).
+   * peer_O[0 .. n_peers): further destinations that receive the SAME bytes with the same strides — replicas of the
+   * output on other GPUs (device pointers mapped through qmha_ipc_open / peer access; NVLink stores issued by the
+   * epilogue's TMA, tile by tile, while the rest of the grid still computes) or on the same device.  The writes are
+   * complete when the launch is; ordering against the peers' own streams is the caller's (see sharding.py). */
+  int64_t o_row_stride, o_batch_stride;
+  int n_peers;              /* 0 .. QMHA_MAX_PEERS                                                       */
+  void* peer_O[7];
 } qmha_args;
+#define QMHA_MAX_PEERS 7
 void qmha_args_init(qmha_args* a);
 int qmha_forward_ex(const qmha_args* a);   /* asynchronous, stream-ordered like qmha_forward             */
 
@@ -198,6 +209,20 @@ int qmha_debug_sm_spans(unsigned long long* out, int n_sms, int reset);
  * start); qmha_args.rope / the *_ex entries choose per call. */
 int qmha_set_rope(int enable, float base);
 int qmha_get_rope(void);
+
+/* ---- peer memory (for qmha_args.peer_O) -------------------------------------------------------
+ * One process per GPU: the owner of a device allocation exports it, the other ranks open it and get a device
+ * pointer that is valid in THEIR process (CUDA IPC over NVLink / NVSwitch peer mappings).
+ *   qmha_ipc_export: dev_ptr may point anywhere inside a cudaMalloc'ed allocation (a torch tensor's data_ptr()
+ *                    works when the allocator does not use expandable segments); handle = 64 opaque bytes,
+ *                    *offset = distance of dev_ptr from the allocation's base.
+ *   qmha_ipc_open:   maps the allocation on the CURRENT device of the calling process and returns base + offset;
+ *                    the mapping is cached per handle and released by qmha_ipc_close_all() / qmha_shutdown().
+ * Several devices in ONE process need no handles: qmha_enable_peer_access(dev, peer) once per ordered pair. */
+int qmha_ipc_export(const void* dev_ptr, unsigned char handle[64], int64_t* offset);
+int qmha_ipc_open(const unsigned char handle[64], int64_t offset, void** dev_ptr);
+int qmha_ipc_close_all(void);
+int qmha_enable_peer_access(int dev, int peer);
 
 /* ---- housekeeping -------------------------------------------------------------------------- */
 const char* qmha_last_error(void);          /* "" when the last call on this thread succeeded */

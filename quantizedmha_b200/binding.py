@@ -30,7 +30,12 @@ class QmhaArgs(C.Structure):
     _fields_ = [("struct_size", C.c_size_t), ("Q", C.c_void_p), ("K", C.c_void_p), ("V", C.c_void_p), ("O", C.c_void_p),
                 ("B", C.c_int), ("N", C.c_int), ("d_model", C.c_int), ("h", C.c_int), ("kernel", C.c_int),
                 ("gran", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("rope", C.c_int),
-                ("rope_base", C.c_float), ("variant", C.c_int), ("stream", C.c_void_p)]
+                ("rope_base", C.c_float), ("variant", C.c_int), ("stream", C.c_void_p),
+                ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64), ("n_peers", C.c_int),
+                ("peer_O", C.c_void_p * 7)]
+
+
+MAX_PEERS = 7
 
 
 def declare(L: C.CDLL) -> C.CDLL:
@@ -66,6 +71,11 @@ def declare(L: C.CDLL) -> C.CDLL:
     L.qmha_default_granularity.argtypes = [i, i]
     L.qmha_set_rope.argtypes = [i, f]
     L.qmha_get_rope.argtypes = []
+    if hasattr(L, "qmha_ipc_export"):     # (older builds loaded side by side by the A/B tools lack these)
+        L.qmha_ipc_export.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
+        L.qmha_ipc_open.argtypes = [C.c_char_p, C.c_int64, C.POINTER(vp)]
+        L.qmha_ipc_close_all.argtypes = []
+        L.qmha_enable_peer_access.argtypes = [i, i]
     L.qmha_launch_count.restype = C.c_int64
     L.qmha_version.restype = C.c_char_p
     L.qmha_shutdown.restype = None
@@ -173,18 +183,35 @@ def solve(Q, K, V, N: int, d_model: int, h: int, out=None):
     return out
 
 
+def _out_strides(out, B: int, N: int, d_model: int) -> Tuple[int, int]:
+    """(row stride, batch stride) in elements of an output tensor that may be a (batch, head-range) slab view of
+    a larger tensor: the last dimension must be contiguous."""
+    if tuple(out.shape) not in ((N, d_model), (B, N, d_model)) or (out.dim() == 2 and B != 1):
+        raise QmhaError(f"out has shape {tuple(out.shape)}, expected {(B, N, d_model)}")
+    if d_model > 1 and out.stride(-1) != 1:
+        raise QmhaError("the last dimension of out must be contiguous")
+    ld = out.stride(-2) if N > 1 else d_model
+    bs = out.stride(0) if (out.dim() == 3 and B > 1) else N * ld
+    return int(ld), int(bs)
+
+
 def forward(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=None, stream=None,
-            rope=None, rope_base: float = 10000.0, out_dtype=None):
+            rope=None, rope_base: float = 10000.0, out_dtype=None, peer_outs=None):
     """Stream-ordered forward on [N, d_model] or [B, N, d_model] CUDA tensors (qmha_forward_ex).
     Q, K, V: float32 like the reference, or float16 / bfloat16 (the quantise pass then reads 2 bytes per
     element); out_dtype: dtype of the result (default: that of Q).  rope: True / False per call, None = the
-    process default (set_rope / QMHA_ROPE).  gran: GRAN_* or -1 = default for the shape."""
+    process default (set_rope / QMHA_ROPE).  gran: GRAN_* or -1 = default for the shape.
+    out may be a slab VIEW of a larger tensor (rows / batch entries strided, last dimension contiguous): the
+    kernel's epilogue writes it in place.  peer_outs: up to 7 further destinations that receive the same bytes
+    with the same strides — raw device addresses (e.g. other ranks' tensors mapped with ipc_open) or tensors
+    shaped and strided like out (replicas on this or on peer-accessible devices)."""
     torch = _torch()
     _check_inputs(Q, K, V, allow16=True)
     Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
     B, N, d_model = _shape3(Q)
     if out is None:
         out = torch.empty(Q.shape, dtype=out_dtype or Q.dtype, device=Q.device)
+    ld, bs = _out_strides(out, B, N, d_model)
     a = QmhaArgs()
     lib().qmha_args_init(C.byref(a))
     a.Q, a.K, a.V, a.O = Q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr()
@@ -194,8 +221,47 @@ def forward(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=N
     a.rope = -1 if rope is None else int(bool(rope))
     a.rope_base = float(rope_base)
     a.stream = _stream_ptr(stream)
+    if (ld, bs) != (d_model, N * d_model):
+        a.o_row_stride, a.o_batch_stride = ld, bs
+    peers = list(peer_outs or [])
+    if len(peers) > MAX_PEERS:
+        raise QmhaError(f"at most {MAX_PEERS} peer outputs")
+    for j, pz in enumerate(peers):
+        if isinstance(pz, int):
+            a.peer_O[j] = pz
+        else:
+            if pz.dtype != out.dtype or _out_strides(pz, B, N, d_model) != (ld, bs):
+                raise QmhaError("peer outputs must have the dtype, shape and strides of out")
+            a.peer_O[j] = pz.data_ptr()
+    a.n_peers = len(peers)
     _check(lib().qmha_forward_ex(C.byref(a)))
     return out
+
+
+def ipc_export(t) -> Tuple[bytes, int]:
+    """(64-byte CUDA IPC handle of the allocation that holds tensor t, byte offset of t inside it) — qmha_ipc_export."""
+    h = C.create_string_buffer(64)
+    off = C.c_int64()
+    _check(lib().qmha_ipc_export(t.data_ptr(), h, C.byref(off)))
+    return h.raw, int(off.value)
+
+
+def ipc_open(handle: bytes, offset: int) -> int:
+    """Device address, valid in THIS process on the current device, of another rank's exported tensor."""
+    if len(handle) != 64:
+        raise QmhaError("a CUDA IPC handle is 64 bytes")
+    p = C.c_void_p()
+    _check(lib().qmha_ipc_open(C.create_string_buffer(handle, 64), offset, C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close_all() -> None:
+    _check(lib().qmha_ipc_close_all())
+
+
+def enable_peer_access(dev: int, peer: int) -> None:
+    """Several devices in one process: lets kernels on `dev` write tensors that live on `peer`."""
+    _check(lib().qmha_enable_peer_access(dev, peer))
 
 
 def flash_solve(Q, K, V, d_model: int, num_heads: int, kernel: str = "fa_tc_int8_b"):

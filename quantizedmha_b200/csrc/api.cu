@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
 #include "../../include/qmha.h"
 #include "attn_fwd.cuh"
 #include "prepare.cuh"
@@ -386,10 +387,19 @@ int attention_variant() {
 
 // scales: [3][B*h] (per-head / per-tensor) or, for gran == QMHA_GRAN_BLOCK, [3][B*h][n_pad/32];
 // aux / vmax: scratch of the same element count used only in block mode.
+// Where the output goes besides the dense [B, N, d_model] default: strides of a slab inside a larger tensor and
+// replicas on peers (qmha_args.o_row_stride / o_batch_stride / peer_O).
+struct OutPlace {
+  long long ld = 0, bs = 0;
+  int n_peers = 0;
+  void* peers[QMHA_MAX_PEERS] = {};
+};
+
 int attention_impl(Workspace* w, const void* Qp, const void* Kp, const void* Vt, const float* scales, void* O,
                    int out_dtype, int B, int N, int d_model, int h, int kernel, cudaStream_t stream,
                    long long* trace = nullptr, int variant = -1, int gran = QMHA_GRAN_HEAD,
-                   float* aux = nullptr, float* vmax = nullptr, unsigned long long* cycles = nullptr) {
+                   float* aux = nullptr, float* vmax = nullptr, unsigned long long* cycles = nullptr,
+                   const OutPlace* place = nullptr) {
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   if (!dtype_ok(out_dtype)) return fail("unknown output dtype");
@@ -405,6 +415,19 @@ int attention_impl(Workspace* w, const void* Qp, const void* Kp, const void* Vt,
   a.trace = trace;
   a.cycles = cycles;
   a.variant = variant >= 0 ? variant : attention_variant();
+  if (place) {
+    if (place->ld < 0 || place->bs < 0) return fail("negative output stride");
+    if (place->ld > 0 && place->ld < d_model) return fail("o_row_stride is smaller than d_model");
+    if (place->bs > 0 && place->bs < (long long)N * (place->ld > 0 ? place->ld : d_model))
+      return fail("o_batch_stride is smaller than N rows");
+    if (place->n_peers < 0 || place->n_peers > QMHA_MAX_PEERS) return fail("n_peers must be 0 .. QMHA_MAX_PEERS");
+    a.o_ld = place->ld; a.o_bs = place->bs; a.n_peers = place->n_peers;
+    for (int i = 0; i < place->n_peers; ++i) {
+      if (!place->peers[i]) return fail("null peer output pointer");
+      if (check_aligned16(place->peers[i], "peer output")) return 1;
+      a.peer_O[i] = place->peers[i];
+    }
+  }
   if (a.int8 && gran == QMHA_GRAN_BLOCK) {
     if (!aux || !vmax) return fail("internal: block mode needs scratch");
     const int units = B * h, nblk = n_pad / 32;
@@ -451,8 +474,11 @@ int forward_device(const qmha_args& a) {
   if (prepare_impl(w, a.Q, a.K, a.V, a.in_dtype, a.B, a.N, a.d_model, a.h, a.kernel, a.gran,
                    rope_from(a.rope, a.rope_base), w->Qp, w->Kp, w->Vt, w->scales, w->amax, s))
     return 1;
+  OutPlace place;
+  place.ld = a.o_row_stride; place.bs = a.o_batch_stride; place.n_peers = a.n_peers;
+  for (int i = 0; i < QMHA_MAX_PEERS && i < a.n_peers; ++i) place.peers[i] = a.peer_O[i];
   if (attention_impl(w, w->Qp, w->Kp, w->Vt, w->scales, a.O, a.out_dtype, a.B, a.N, a.d_model, a.h, a.kernel, s,
-                     nullptr, a.variant, a.gran, w->aux, w->vmax))
+                     nullptr, a.variant, a.gran, w->aux, w->vmax, nullptr, &place))
     return 1;
   g_err.clear();
   return 0;
@@ -878,8 +904,104 @@ int qmha_forward_host_ex(const void* Qv, const void* Kv, const void* Vv, void* O
   return 0;
 }
 
+// ---- peer memory: CUDA IPC mappings of other ranks' output tensors (qmha_args.peer_O) ----------------------
+namespace {
+struct IpcMapping { int dev; void* base; };
+std::map<std::string, IpcMapping> g_ipc;   // key: device number + the 64 handle bytes
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+GetAddressRangeFn get_address_range_fn() {
+  static GetAddressRangeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<GetAddressRangeFn>(p);
+  }
+  return fn;
+}
+int close_ipc_locked() {
+  int rc = 0, cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : g_ipc) {
+    cudaSetDevice(kv.second.dev);
+    if (cudaIpcCloseMemHandle(kv.second.base) != cudaSuccess) rc = 1;
+  }
+  g_ipc.clear();
+  cudaSetDevice(cur);
+  cudaGetLastError();
+  return rc;
+}
+}  // namespace
+
+int qmha_ipc_export(const void* dev_ptr, unsigned char handle[64], int64_t* offset) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (!dev_ptr || !handle || !offset) return fail("qmha_ipc_export: null argument");
+  if (require_device() < 0) return 1;
+  GetAddressRangeFn range = get_address_range_fn();
+  if (!range) return fail("cuMemGetAddressRange entry point not available");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, (CUdeviceptr)(uintptr_t)dev_ptr) != CUDA_SUCCESS)
+    return fail("qmha_ipc_export: not a device allocation");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base));
+  if (e != cudaSuccess) cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda("cudaIpcGetMemHandle (allocations from expandable segments / cudaMallocAsync pools cannot be exported)", e);
+  memcpy(handle, &h, 64);
+  *offset = (int64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+  g_err.clear();
+  return 0;
+}
+
+int qmha_ipc_open(const unsigned char handle[64], int64_t offset, void** dev_ptr) {
+  if (!handle || !dev_ptr || offset < 0) return fail("qmha_ipc_open: bad argument");
+  const int dev = require_device();
+  if (dev < 0) return 1;
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::string key(reinterpret_cast<const char*>(handle), 64);
+  key.push_back((char)dev);
+  auto it = g_ipc.find(key);
+  if (it == g_ipc.end()) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail_cuda("cudaIpcOpenMemHandle", e); }
+    it = g_ipc.emplace(key, IpcMapping{dev, base}).first;
+  }
+  *dev_ptr = static_cast<char*>(it->second.base) + offset;
+  g_err.clear();
+  return 0;
+}
+
+int qmha_ipc_close_all(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (close_ipc_locked()) return fail("cudaIpcCloseMemHandle failed");
+  return 0;
+}
+
+int qmha_enable_peer_access(int dev, int peer) {
+  if (require_device() < 0) return 1;
+  if (dev == peer) return 0;
+  int can = 0;
+  cudaError_t e = cudaDeviceCanAccessPeer(&can, dev, peer);
+  if (e != cudaSuccess) return fail_cuda("cudaDeviceCanAccessPeer", e);
+  if (!can) return fail("device " + std::to_string(dev) + " cannot access device " + std::to_string(peer) + " directly");
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(dev);
+  e = cudaDeviceEnablePeerAccess(peer, 0);
+  cudaSetDevice(cur);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+  if (e != cudaSuccess) return fail_cuda("cudaDeviceEnablePeerAccess", e);
+  g_err.clear();
+  return 0;
+}
+
 void qmha_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
+  close_ipc_locked();
   int cur = 0;
   cudaGetDevice(&cur);
   for (auto& kv : g_ws) {

@@ -143,6 +143,13 @@ struct Cfg {
   static constexpr uint32_t kIdescPVbf = make_idesc(kAccF32, kFmtBF16, kFmtBF16, kBM, kD);
 };
 
+// Output tensor maps of the peer destinations (qmha_args.peer_O): the epilogue repeats every TMA tensor store of the
+// staged tile once per peer, so a replica of the output lands in the other GPUs' memory over NVLink while the rest of
+// the grid still computes (the "gather" of a sharded forward costs no extra pass and no extra kernel).
+struct PeerMaps {
+  CUtensorMap m[kMaxPeers];
+};
+
 struct Barriers {
   uint64_t q_full;
   uint64_t k_full[4], k_empty[4];
@@ -474,7 +481,7 @@ template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
-                AttnParams prm) {
+                const __grid_constant__ PeerMaps tm_peers, AttnParams prm) {
   using C = Cfg<kInt8, kD, kPv8>;
   // lazy rescale: the reference max is raised when a row max exceeds it by more than this many log2 units.  fp16 P
   // holds 2^4 with full relative precision; 8-bit P codes are rn(127.5 p), so p must stay <= 2.
@@ -1075,9 +1082,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int b = unit / prm.H, head = unit % prm.H;
     const int osz = prm.out_dtype == 0 ? 4 : 2;   // output element size
     auto pack16 = [&](float lo, float hi) { return prm.out_dtype == 2 ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi); };
-    char* out_b = reinterpret_cast<char*>(prm.O) +
-                  (((size_t)b * prm.N + row) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d) * osz;
-    float* out = reinterpret_cast<float*>(out_b);
+    // O may be a slab of a larger tensor: row / batch strides come from the caller (dense: H*d, N*H*d)
+    const size_t out_off = ((size_t)b * (size_t)prm.o_bs + (size_t)row * (size_t)prm.o_ld + (size_t)head * prm.d) * osz;
+    // destination 0 is O itself, 1 .. n_peers the replicas (same strides, same bytes)
+    auto dest = [&](int pe) { return reinterpret_cast<char*>(pe == 0 ? prm.O : prm.peer_O[pe - 1]); };
     const bool row_ok = row < prm.N;
     const bool vec_ok = (prm.d & 3) == 0;
     constexpr bool kStaged = C::kTileBytesQK >= 16384;
@@ -1141,6 +1149,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         __syncwarp();
         if (lane == 0 && row0 < prm.N && ch * 32 < prm.d) {
           tma_store_3d(&tm_o, buf, head * prm.d + ch * 32, row0, b);
+#pragma unroll 1
+          for (int pe = 0; pe < prm.n_peers; ++pe)   // replicas: the same staged tile, once per peer (NVLink)
+            tma_store_3d(&tm_peers.m[pe], buf, head * prm.d + ch * 32, row0, b);
           bulk_commit_group();
         }
       }
@@ -1153,7 +1164,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float* stage = reinterpret_cast<float*>(sQ + t * C::kTileBytesQK) + (warp & 3) * 1024;  // 32 x 32 floats
       const int r_sub = lane >> 3, c4 = lane & 7;
       const int row0 = q_base + t * kBM + (warp & 3) * 32;          // first row of this warp
-      float* out0 = reinterpret_cast<float*>(prm.O) + ((size_t)b * prm.N + row0) * ((size_t)prm.H * prm.d) + (size_t)head * prm.d;
+      const size_t off0 = (size_t)b * (size_t)prm.o_bs + (size_t)row0 * (size_t)prm.o_ld + (size_t)head * prm.d;
       constexpr int kChunks = kD / 32;
       uint32_t o[kChunks][32];
 #pragma unroll
@@ -1173,8 +1184,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + r_sub;
           const float4 v = *reinterpret_cast<const float4*>(stage + r * 32 + ((c4 ^ (r & 7)) << 2));
-          if (row0 + r < prm.N && col < prm.d)
-            *reinterpret_cast<float4*>(out0 + (size_t)r * ((size_t)prm.H * prm.d) + col) = v;
+          if (row0 + r < prm.N && col < prm.d) {
+#pragma unroll 1
+            for (int pe = 0; pe <= prm.n_peers; ++pe)
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(dest(pe)) + off0 + (size_t)r * (size_t)prm.o_ld + col) = v;
+          }
         }
         __syncwarp();
       }
@@ -1184,6 +1198,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t o[32];
         tmem_ld32(tO + ch * 32, o);
         tmem_wait_ld();
+#pragma unroll 1
+       for (int pe = 0; pe <= prm.n_peers; ++pe) {
+        char* out_b = dest(pe) + out_off;
+        float* out = reinterpret_cast<float*>(out_b);
         if (row_ok && prm.out_dtype != 0) {   // 16-bit output without TMA: pairs when d is even, scalars otherwise
           uint16_t* o16 = reinterpret_cast<uint16_t*>(out_b);
           if ((prm.d & 1) == 0) {
@@ -1219,6 +1237,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           }
         }
+       }
       }
     }
   }
@@ -1293,12 +1312,12 @@ bool make_map_2d(CUtensorMap* m, const void* base, int elt, uint64_t rows, uint6
 // 3D output tensor [d2][d1][d0] (d0 contiguous), box = [1][box1][box0]; out_dtype 0 = fp32 (SWIZZLE_128B,
 // box0 * 4 == 128), 1 = fp16 / 2 = bf16 (SWIZZLE_64B, box0 * 2 == 64).
 bool make_map_3d_out(CUtensorMap* m, const void* base, int out_dtype, uint64_t d0, uint64_t d1, uint64_t d2,
-                     uint32_t box0, uint32_t box1, std::string* err) {
+                     uint64_t ld1, uint64_t ld2, uint32_t box0, uint32_t box1, std::string* err) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
   const uint64_t elt = out_dtype == 0 ? 4 : 2;
   const cuuint64_t gdim[3] = {d0, d1, d2};
-  const cuuint64_t gstride[2] = {d0 * elt, d0 * d1 * elt};
+  const cuuint64_t gstride[2] = {ld1 * elt, ld2 * elt};   // row / batch pitch (dense: d0, d0 * d1 elements)
   const cuuint32_t box[3] = {box0, box1, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapDataType dt = out_dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -1326,9 +1345,24 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   // output tensor map for the TMA-store epilogue (only when a 32-column chunk never straddles a head)
   CUtensorMap to;
   memset(&to, 0, sizeof(to));
-  const bool tma_store = (a.d % 32) == 0 && getenv("QMHA_NO_TMA_STORE") == nullptr;
-  if (tma_store && !make_map_3d_out(&to, a.O, a.out_dtype, (uint64_t)a.H * a.d, (uint64_t)a.N, (uint64_t)a.B, 32, 32, err))
-    return false;
+  PeerMaps peers;
+  memset(&peers, 0, sizeof(peers));
+  const uint64_t o_ld = a.o_ld > 0 ? (uint64_t)a.o_ld : (uint64_t)a.H * a.d;
+  const uint64_t o_bs = a.o_bs > 0 ? (uint64_t)a.o_bs : (uint64_t)a.N * o_ld;
+  const uint64_t o_elt = a.out_dtype == 0 ? 4 : 2;
+  if (a.n_peers < 0 || a.n_peers > kMaxPeers) { *err = "n_peers out of range"; return false; }
+  // tensor maps need 16-byte multiples for the pitches (and the plain paths store 16 bytes at a time)
+  const bool pitch_ok = (o_ld * o_elt) % 16 == 0 && (o_bs * o_elt) % 16 == 0;
+  if ((a.o_ld > 0 || a.o_bs > 0) && !pitch_ok) { *err = "output row / batch strides must be multiples of 16 bytes"; return false; }
+  const bool tma_store = (a.d % 32) == 0 && pitch_ok && getenv("QMHA_NO_TMA_STORE") == nullptr;
+  if (tma_store) {
+    if (!make_map_3d_out(&to, a.O, a.out_dtype, (uint64_t)a.H * a.d, (uint64_t)a.N, (uint64_t)a.B, o_ld, o_bs, 32, 32, err))
+      return false;
+    for (int pe = 0; pe < a.n_peers; ++pe)
+      if (!make_map_3d_out(&peers.m[pe], a.peer_O[pe], a.out_dtype, (uint64_t)a.H * a.d, (uint64_t)a.N, (uint64_t)a.B,
+                           o_ld, o_bs, 32, 32, err))
+        return false;
+  }
   auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb, kBf16, kPv8>;
   // block mode keeps one float4 of constants per 32-key block of the unit behind the barriers
   const size_t smem_bytes = (size_t)C::kSmemBytes + (kBlk ? (size_t)(a.n_pad / 32) * 16 : 0);
@@ -1362,8 +1396,12 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.tma_store = tma_store ? 1 : 0;
   p.one = 1;
   p.cycles = a.cycles;
+  p.o_ld = (long long)o_ld;
+  p.o_bs = (long long)o_bs;
+  p.n_peers = a.n_peers;
+  for (int pe = 0; pe < kMaxPeers; ++pe) p.peer_O[pe] = pe < a.n_peers ? a.peer_O[pe] : nullptr;
   dim3 grid((a.N + 2 * kBM - 1) / (2 * kBM), (unsigned)units, 1);
-  kern<<<grid, kThreads, smem_bytes, a.stream>>>(tq, tk, tv, to, p);
+  kern<<<grid, kThreads, smem_bytes, a.stream>>>(tq, tk, tv, to, peers, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("attention launch: ") + cudaGetErrorString(e); return false; }
   return true;

@@ -8,6 +8,7 @@ namespace qmha {
 
 constexpr int kCycleSms = 192;                     // per-SM slots of the development cycle counters
 constexpr int kCycleWords = 2 + 2 * kCycleSms;     // {sum, CTAs, per SM: ~earliest start, latest end}
+constexpr int kMaxPeers = 7;                       // further destinations of the output (qmha_args.peer_O)
 
 struct AttnParams {
   void* O;              // [B, N, H*d] fp32 / fp16 / bf16 (out_dtype)
@@ -30,6 +31,9 @@ struct AttnParams {
   int tma_store;        // epilogue writes the output with TMA tensor stores (needs d % 32 == 0)
   int one;              // 1 (a value the compiler cannot fold; see i2f_magic)
   unsigned long long* cycles;  // development aid: {sum of CTA residency clocks, CTA count} or nullptr
+  long long o_ld, o_bs; // distance between consecutive rows / batch entries of O in elements (dense: H*d, N*H*d)
+  int n_peers;          // further destinations that receive the same bytes (replicas on NVLink peers)
+  void* peer_O[kMaxPeers];
 };
 
 struct AttnLaunch {
@@ -53,6 +57,9 @@ struct AttnLaunch {
   bool bf16 = false;    // 16-bit kernel with bf16 operands (Qp / Kp / Vt hold bf16)
   bool pv8 = false;     // INT8 kernel with INT8 P.V: Vt holds int8 codes [units, d_pad, n_pad], P goes to the MMA as 8-bit codes
   cudaStream_t stream;
+  long long o_ld = 0, o_bs = 0;   // 0 = dense
+  int n_peers = 0;
+  void* peer_O[kMaxPeers] = {};
   bool units_y_limit_exceeded() const { return (long long)B * H > 65535; }
 };
 

@@ -141,3 +141,89 @@ def forward_sharded(Q, K, V, H: int, kernel="int8", gran: int = -1, chunks: int 
                 out[b, :, h0 * d:h1 * d] = seg.permute(1, 0, 2).reshape(N, (h1 - h0) * d)
                 j += h1 - h0
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Fused gather: the attention kernel's epilogue writes every finished output tile into the
+# replicas of ALL ranks — TMA tensor stores into NVLink peer memory, issued tile by tile while the rest of the
+# grid still computes — so the replicated result costs no all-gather, no extra pass over the output and no
+# extra kernel.  NCCL only carries two tiny stream-ordered all-reduces that fence the replicas' reuse.
+
+def launch_plan(B: int, H: int, world: int, rank: int) -> List[Tuple[int, int, int, int]]:
+    """This rank's units as kernel launches [(b0, b1, h0, h1)]: heads h0..h1-1 of batch entries b0..b1-1.
+    Consecutive whole batch entries are merged into one launch; partial head ranges stay one launch each."""
+    plan: List[Tuple[int, int, int, int]] = []
+    for b, h0, h1 in shard_slabs(B, H, world, rank):
+        if plan and h0 == 0 and h1 == H and plan[-1][2] == 0 and plan[-1][3] == H and plan[-1][1] == b:
+            plan[-1] = (plan[-1][0], b + 1, 0, H)
+        else:
+            plan.append((b, b + 1, h0, h1))
+    return plan
+
+
+def slab_offset(b0: int, h0: int, N: int, H: int, d: int) -> int:
+    """Element offset of out[b0, 0, h0*d] inside a contiguous [B, N, H*d] tensor."""
+    return (b0 * N * H + h0) * d
+
+
+class ReplicatedOutput:
+    """One [B, N, H*d] output tensor per rank, every rank's copy mapped into every other rank's address space
+    (CUDA IPC handles exchanged through the process group; the mappings stay open until close()).
+    `local` is this rank's tensor, `peer_base[r]` the device address of rank r's tensor in THIS process."""
+
+    def __init__(self, B: int, N: int, H: int, d: int, dtype=None, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import binding as qb
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world - 1 > qb.MAX_PEERS:
+            raise qb.QmhaError(f"at most {qb.MAX_PEERS + 1} ranks")
+        self.B, self.N, self.H, self.d = B, N, H, d
+        self.local = torch.empty((B, N, H * d), dtype=dtype or torch.float32, device=device)
+        mine = qb.ipc_export(self.local)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        self.peer_base = {r: qb.ipc_open(h, off) for r, (h, off) in enumerate(handles) if r != self.rank}
+        self._fence = torch.zeros(1, dtype=torch.int32, device=self.local.device)
+
+    def fence(self):
+        """Stream-ordered rendezvous of all ranks (one 4-byte NCCL all-reduce on the current stream): everything
+        the ranks enqueued before it — kernels that write into the replicas, kernels that read them — is complete
+        on every rank before anything enqueued after it starts."""
+        import torch.distributed as dist
+        dist.all_reduce(self._fence, group=self.group)
+
+    def close(self):
+        from . import binding as qb
+        self.peer_base = {}
+        qb.ipc_close_all()
+
+
+def forward_fused_gather(Q, K, V, H: int, rep: "ReplicatedOutput", kernel="int8", gran: int = -1, forward_fn=None,
+                         fence: bool = True):
+    """Sharded forward with a replicated result and NO gather step: Q, K, V [B, N, H*d] are present on every
+    rank, rank r computes only its own (batch x head) units and its attention kernel stores each finished tile
+    into rep.local AND into every peer's replica (qmha_args.peer_O).  Returns rep.local, complete on the current
+    stream once the trailing fence has passed.
+
+    forward_fn(q, k, v, heads, out_view, peer_addrs) is injected by the CPU tests; the default is the library's
+    forward on CUDA tensors."""
+    B, N, d = Q.shape[0], Q.shape[1], Q.shape[2] // H
+    if forward_fn is None:
+        from . import binding as qb
+        forward_fn = lambda q, k, v, heads, out_view, peers: qb.forward(q, k, v, heads, kernel=kernel, gran=gran,
+                                                                         out=out_view, peer_outs=peers)
+    out = rep.local
+    esz = out.element_size()
+    if fence:
+        rep.fence()                      # nobody still reads the previous contents of any replica
+    for b0, b1, h0, h1 in launch_plan(B, H, rep.world, rep.rank):
+        q, k, v = (t[b0:b1, :, h0 * d:h1 * d].contiguous() for t in (Q, K, V))
+        view = out[b0:b1, :, h0 * d:h1 * d]
+        off = slab_offset(b0, h0, N, H, d) * esz
+        peers = [rep.peer_base[r] + off for r in sorted(rep.peer_base)]
+        forward_fn(q, k, v, h1 - h0, view, peers)
+    if fence:
+        rep.fence()                      # every rank's stores into this replica have landed
+    return out

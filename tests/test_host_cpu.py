@@ -141,10 +141,51 @@ fwd = lambda a, b, c, heads: torch.from_numpy(orc.mha(a.numpy(), b.numpy(), c.nu
 for chunks in (1, 2, 5):
     o = forward_sharded(torch.from_numpy(q), torch.from_numpy(k), torch.from_numpy(v), H, chunks=chunks, forward_fn=fwd)
     assert np.array_equal(o.numpy(), full), f"forward_sharded(chunks={{chunks}}) differs from the unsharded oracle"
+# fused gather (sharding.forward_fused_gather): every rank's launch plan writes its slabs into ALL replicas.  The
+# replicas are file-backed shared memory here and a "peer address" is (rank + 1) << 40 | byte offset, so the slab
+# offsets and strides the kernel would get are exercised across real processes; the fences run over gloo.
+from quantizedmha_b200.sharding import forward_fused_gather
+shape = (B, N, H * d)
+paths = [os.path.join(os.environ["REP_DIR"], "rep%d.bin" % r) for r in range(world)]
+np.memmap(paths[rank], dtype=np.float32, mode="w+", shape=shape)[...] = np.nan
+dist.barrier()
+mm = [np.memmap(p, dtype=np.float32, mode="r+", shape=shape) for p in paths]
+class Rep:
+    pass
+rep = Rep()
+rep.world, rep.rank, rep.local = world, rank, torch.from_numpy(mm[rank])
+rep.peer_base = dict((r, (r + 1) << 40) for r in range(world) if r != rank)
+rep.fence = dist.barrier
+def fused(qs, ks, vs, heads, out_view, peers):
+    o = orc.mha(qs.numpy(), ks.numpy(), vs.numpy(), heads, threads=1)
+    out_view.copy_(torch.from_numpy(o))
+    assert len(peers) == world - 1
+    for addr in peers:
+        r, off = (addr >> 40) - 1, (addr & ((1 << 40) - 1)) // 4
+        dst = np.lib.stride_tricks.as_strided(mm[r].reshape(-1)[off:], shape=o.shape, strides=(N * H * d * 4, H * d * 4, 4))
+        dst[...] = o
+for Bx in (B,):
+    o = forward_fused_gather(torch.from_numpy(q), torch.from_numpy(k), torch.from_numpy(v), H, rep, forward_fn=fused)
+    assert np.array_equal(np.asarray(mm[rank]), full), "fused gather: this rank's replica differs from the unsharded oracle"
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
 """
+
+
+def test_fused_gather_launch_plan_covers_every_unit_once():
+    from quantizedmha_b200.sharding import launch_plan, slab_offset, unit_range
+    for B, H, W in [(8, 32, 8), (32, 32, 8), (8, 32, 3), (1, 8, 2), (5, 7, 4), (2, 3, 8)]:
+        seen = []
+        for r in range(W):
+            plan = launch_plan(B, H, W, r)
+            got = [b * H + h for (b0, b1, h0, h1) in plan for b in range(b0, b1) for h in range(h0, h1)]
+            assert got == list(range(*unit_range(B * H, W, r)))
+            assert all(b1 - b0 == 1 or (h0, h1) == (0, H) for (b0, b1, h0, h1) in plan)   # only whole entries are merged
+            seen += got
+        assert seen == list(range(B * H))
+    assert launch_plan(32, 32, 8, 7) == [(28, 32, 0, 32)]          # C5 over 8 GPUs: one launch per rank
+    assert slab_offset(2, 3, 100, 8, 16) == (2 * 100 * 8 + 3) * 16
 
 
 def test_two_rank_sharding_over_gloo(tmp_path):
@@ -155,7 +196,8 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     port = 29500 + (os.getpid() % 400)
     procs = []
     for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   REP_DIR=str(tmp_path))
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT))
     for p in procs:

@@ -8,7 +8,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import quantizedmha_b200 as qm
-from quantizedmha_b200.sharding import shard_slabs, slab_view, gather_outputs, forward_sharded
+from quantizedmha_b200.sharding import (shard_slabs, slab_view, gather_outputs, forward_sharded, forward_fused_gather,
+                                        ReplicatedOutput)
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -41,6 +42,24 @@ for chunks in (1, 3):
     ok = ok and same
     if rank == 0:
         print(f"forward_sharded(chunks={chunks}) == single-GPU forward: {same}", flush=True)
+# fused gather: no collective at all — the attention epilogue stores every finished tile into the replicas of ALL
+# ranks (TMA tensor stores into CUDA-IPC mapped peer memory over NVLink); NCCL only carries two 4-byte fences
+for kernel, gran, odt in (("int8", qm.GRAN_BLOCK, torch.float32), ("f16", qm.GRAN_HEAD, torch.float32),
+                          ("int8", qm.GRAN_BLOCK, torch.float16)):
+    rep_out = ReplicatedOutput(B, N, H, d, dtype=odt, device=dev)
+    rep_out.local.fill_(float("nan"))
+    torch.cuda.synchronize()
+    for it in range(2):                                    # the second pass reuses the replicas behind the fence
+        out = forward_fused_gather(q, k, v, H, rep_out, kernel=kernel, gran=gran)
+    full = qm.forward(q, k, v, H, kernel=kernel, gran=gran, out_dtype=odt)
+    torch.cuda.synchronize()
+    qm.binding.check_async_error()
+    same = bool(torch.equal(out, full))
+    ok = ok and same
+    if rank == 0:
+        print(f"forward_fused_gather({kernel}, gran={gran}, {odt}) == single-GPU forward: {same}", flush=True)
+    dist.barrier()
+    rep_out.close()
 # timing at a BASELINE-sized shape: 8 batch entries of C4 split over the ranks, result replicated on every rank
 Bt, Ht, Nt, dt = 8, 32, 8192, 128
 gen = torch.Generator(device=dev).manual_seed(99)
@@ -61,6 +80,18 @@ t_comp = timed(compute_only)
 t_1 = timed(lambda: forward_sharded(qt, kt, vt, Ht, kernel="int8", gran=qm.GRAN_BLOCK, chunks=1))
 t_4 = timed(lambda: forward_sharded(qt, kt, vt, Ht, kernel="int8", gran=qm.GRAN_BLOCK, chunks=4))
 t_8 = timed(lambda: forward_sharded(qt, kt, vt, Ht, kernel="int8", gran=qm.GRAN_BLOCK, chunks=8))
+rep_t = ReplicatedOutput(Bt, Nt, Ht, dt, dtype=torch.float32, device=dev)
+t_f = timed(lambda: forward_fused_gather(qt, kt, vt, Ht, rep_t, kernel="int8", gran=qm.GRAN_BLOCK))
+full_t = qm.forward(qt, kt, vt, Ht, kernel="int8", gran=qm.GRAN_BLOCK)
+torch.cuda.synchronize()
+same = bool(torch.equal(rep_t.local, full_t))
+ok = ok and same
+rep_16 = ReplicatedOutput(Bt, Nt, Ht, dt, dtype=torch.float16, device=dev)
+t_f16 = timed(lambda: forward_fused_gather(qt, kt, vt, Ht, rep_16, kernel="int8", gran=qm.GRAN_BLOCK))
+if rank == 0:
+    print(f"C4 split over {world} ranks, FUSED gather (epilogue stores into every replica over NVLink, no all-gather): "
+          f"{t_f:.2f} ms with the fp32 result replicated (== single-GPU forward: {same}), {t_f16:.2f} ms with an fp16 result",
+          flush=True)
 if rank == 0:
     gb = Bt * Nt * Ht * dt * 4 / 1e9
     print(f"C4 split over {world} ranks, replicated {gb:.2f} GB result: own slabs only {t_comp:.2f} ms; "
