@@ -82,6 +82,14 @@ static_assert((QMHA_SOFT_RING == 0 && QMHA_LAZY_PV == 0) || kMmaSplit == 2, "wri
 #define QMHA_BIAS_MMA 1
 #endif
 constexpr bool kBiasMma = QMHA_BIAS_MMA != 0;
+// Persistent INT8 d = 128 kernel (see attn_fwd_kernel, kPersist): 0 = off unless QMHA_PERSIST=1, 1 = on unless QMHA_PERSIST=0.
+// Built, bit-identical, and measured SLOWER than one CTA per item at C4 (187.9 k against 181.0 k clk per item): the gaps
+// between CTAs, the setup and the first-scores latency do disappear (1.6 k clk per item against the same code run with one
+// item per CTA), but ptxas schedules the main loop of the nested form 4.8 % slower (189.5 k clk with one item per CTA; same
+// instruction counts for the arithmetic, more integer / predicate work around it).  Opt-in.
+#ifndef QMHA_DEFAULT_PERSIST
+#define QMHA_DEFAULT_PERSIST 0
+#endif
 constexpr int kBiasTileBytes = 4096 + 2048;   // A: 128 rows x 32 B, B: 64 rows x 32 B (fp16, SWIZZLE_32B layout)
 constexpr int kAllocWarp = 8;
 constexpr int kTmaWarp = 9;
@@ -157,7 +165,8 @@ struct Barriers {
   uint64_t s_full[2][2], p_full[2][2], pv_done[2][2];  // [tile][buffer / step parity]
   uint64_t o_final[2];                              // one-shot: last P·V of the tile retired
   uint64_t s0_read[2];                              // one-shot: S_t(0) copied to registers
-  uint64_t qk_done;                                 // one-shot: every Q·K^T of the CTA retired (K ring is free)
+  uint64_t qk_done;                                 // once per item: every Q·K^T of the item retired (K ring, Q tile free)
+  uint64_t epi_done;                                // persistent kernel, once per item: the output stores have read their staging tiles (V^T ring free)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -476,8 +485,15 @@ __device__ __forceinline__ void tile_row_exp_blk(const uint32_t (&s)[kHN], uint3
   }
 }
 
+// kPersist: one CTA per SM walks the work items (unit, 256-row query block) item0, item0 + gridDim.x, ... instead of one
+// CTA per item.  The mbarriers, the TMEM allocation and the constant tiles live for the whole kernel; every role loops
+// over the items on its own, so the producers prefetch Q and the K tiles of the next item and the MMA warps issue its first
+// scores while the softmax warps still write the previous output (which is staged in the V^T ring only: the K ring and the
+// Q tile are free by then).  Barrier phases continue across items: the rings run on the global tile number J0 + j, the
+// once-per-item barriers on the item number k; N is a multiple of 256 (four half-steps), so s_full / p_full and the score
+// buffers start every item exactly as they start the first one.
 template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25, bool kBf16 = false,
-          bool kPv8 = false>
+          bool kPv8 = false, bool kPersist = false>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -489,6 +505,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr bool kSoftRing = QMHA_SOFT_RING == 2 || (QMHA_SOFT_RING == 1 && !kInt8);
   constexpr bool kLazyPv = QMHA_LAZY_PV == 2 || (QMHA_LAZY_PV == 1 && !kInt8);
   static_assert(!kBf16 || !kInt8, "bf16 is a variant of the 16-bit kernel");
+  static_assert(!kPersist || (kMmaSplit == 2 && kLazyPv && !kSoftRing && !kTrace), "persistent kernel: two-warp MMA issue, lazy pv_done, committed rings");
   constexpr uint32_t kIdQK = kBf16 ? C::kIdescQKbf : C::kIdescQK;
   constexpr uint32_t kIdPV = kBf16 ? C::kIdescPVbf : C::kIdescPV;
   extern __shared__ uint8_t smem_raw[];
@@ -500,12 +517,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sV = sK + C::kStagesK * C::kTileBytesQK;
   uint8_t* sBias = sV + C::kStagesV * C::kTileBytesV;   // constant operand tiles of the bias MMA (INT8 kernels)
   Barriers* bars = reinterpret_cast<Barriers*>(sBias + (C::kBias ? kBiasTileBytes : 0));
-  float4* blk_tab = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 512);  // block mode only
+  float4* blk_tab0 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 512);  // block mode only (persistent: two tables)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int unit = blockIdx.y;                 // b * H + head
-  const int q_base = blockIdx.x * (2 * kBM);   // first query row of this CTA
+  // work items of this CTA: item0, item0 + item_stride, ... (one item without kPersist); every role keeps its own
+  // copy of (unit, q_base) because the roles run up to one item apart
+  const int nqb = kPersist ? prm.n_qblocks : 1;
+  const int n_items = kPersist ? prm.n_items : 1;
+  const int item0 = kPersist ? (int)blockIdx.x : 0;
+  const int item_stride = kPersist ? (int)gridDim.x : 1;
+  int unit = kPersist ? item0 / nqb : (int)blockIdx.y;                        // b * H + head
+  int q_base = (kPersist ? item0 % nqb : (int)blockIdx.x) * (2 * kBM);        // first query row of the item
+  auto set_item = [&](int it) {
+    if constexpr (kPersist) { unit = it / nqb; q_base = (it % nqb) * (2 * kBM); }
+  };
   const int n_tiles = prm.n_kv_tiles;
   const ErrCtx err_flag{prm.error_flag, prm.error_host, prm.launch_id};
   bool dead = false;
@@ -540,6 +566,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&bars->s0_read[t], 128);
     }
     mbar_init(&bars->qk_done, kMmaSplit);
+    mbar_init(&bars->epi_done, 8);
     fence_mbar_init();
     if constexpr (kMmaSplit == 2) {
       // Q and the first K tiles are requested right here, before the CTA-wide barrier: the TMEM
@@ -580,34 +607,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsService));
    if (kMmaSplit == 2 && warp == kTmaWarp) {
     // ======================================================================== TMA producer: Q, K ring
-    if (lane == 0) {  // Q and K tiles 0 .. kStagesK-1 were requested during the CTA setup
-      const int k_row0 = unit * prm.n_pad;
-      for (int j = C::kStagesK; j < n_tiles; ++j) {
-        const int st = j % C::kStagesK;
-        const uint32_t ph = (uint32_t)(j / C::kStagesK);
-        if (j >= C::kStagesK) mbar_wait(&bars->k_empty[st], (ph - 1) & 1, err_flag, 101, dead);
-        if (QMHA_KO & 32) { mbar_arrive(&bars->k_full[st]); continue; }   // timing experiment: no K traffic after the first ring fill
-        mbar_arrive_expect_tx(&bars->k_full[st], C::kTileBytesQK);
+    if (lane == 0) {  // Q and K tiles 0 .. kStagesK-1 of the first item were requested during the CTA setup
+      int k = 0;
+      for (int it = item0; it < n_items && !dead; it += item_stride, ++k) {
+        if (kPersist && k > 0) {
+          set_item(it);
+          // the Q tiles are dead once every Q.K^T of the previous item has retired
+          mbar_wait(&bars->qk_done, (uint32_t)(k - 1) & 1, err_flag, 103, dead);
+          mbar_arrive_expect_tx(&bars->q_full, 2 * C::kTileBytesQK);
 #pragma unroll
-        for (int sub = 0; sub < C::kSubQK; ++sub)
-          tma_load_2d(sK + st * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_k, &bars->k_full[st],
-                      sub * (C::kAtomQK / C::kEltQK), k_row0 + j * kBN);
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int sub = 0; sub < C::kSubQK; ++sub)
+              tma_load_2d(sQ + t * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_q, &bars->q_full,
+                          sub * (C::kAtomQK / C::kEltQK), unit * prm.n_pad + q_base + t * kBM);
+        }
+        const int k_row0 = unit * prm.n_pad;
+        const int J0 = k * n_tiles;
+        for (int j = (k == 0 ? C::kStagesK : 0); j < n_tiles; ++j) {
+          const int J = J0 + j;
+          const int st = J % C::kStagesK;
+          const uint32_t ph = (uint32_t)(J / C::kStagesK);
+          if (J >= C::kStagesK) mbar_wait(&bars->k_empty[st], (ph - 1) & 1, err_flag, 101, dead);
+          if (QMHA_KO & 32) { mbar_arrive(&bars->k_full[st]); continue; }   // timing experiment: no K traffic after the first ring fill
+          mbar_arrive_expect_tx(&bars->k_full[st], C::kTileBytesQK);
+#pragma unroll
+          for (int sub = 0; sub < C::kSubQK; ++sub)
+            tma_load_2d(sK + st * C::kTileBytesQK + sub * C::kSubBytesQK, &tm_k, &bars->k_full[st],
+                        sub * (C::kAtomQK / C::kEltQK), k_row0 + j * kBN);
+        }
       }
     }
    } else if (kMmaSplit == 2 && warp == kTmaWarpV) {
     // ======================================================================== TMA producer: V^T ring
     if (lane == 0) {
-      const int v_row = unit * kD;
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % C::kStagesV;
-        const uint32_t ph = (uint32_t)(j / C::kStagesV);
-        if (j >= C::kStagesV) mbar_wait(&bars->v_empty[st], (ph - 1) & 1, err_flag, 102, dead);
-        if ((QMHA_KO & 32) && j >= C::kStagesV) { mbar_arrive(&bars->v_full[st]); continue; }   // same for V^T
-        mbar_arrive_expect_tx(&bars->v_full[st], C::kTileBytesV);
+      int k = 0;
+      for (int it = item0; it < n_items && !dead; it += item_stride, ++k) {
+        if (kPersist && k > 0) {
+          set_item(it);
+          // the previous item's output is staged in this ring: wait until its TMA stores have read the tiles
+          mbar_wait(&bars->epi_done, (uint32_t)(k - 1) & 1, err_flag, 104, dead);
+        }
+        const int v_row = unit * kD;
+        const int J0 = k * n_tiles;
+        for (int j = 0; j < n_tiles; ++j) {
+          const int J = J0 + j;
+          const int st = J % C::kStagesV;
+          const uint32_t ph = (uint32_t)(J / C::kStagesV);
+          if (J >= C::kStagesV) mbar_wait(&bars->v_empty[st], (ph - 1) & 1, err_flag, 102, dead);
+          if ((QMHA_KO & 32) && J >= C::kStagesV) { mbar_arrive(&bars->v_full[st]); continue; }   // same for V^T
+          mbar_arrive_expect_tx(&bars->v_full[st], C::kTileBytesV);
 #pragma unroll
-        for (int sub = 0; sub < C::kSubTilesV; ++sub)
-          tma_load_2d(sV + st * C::kTileBytesV + sub * C::kSubBytesV, &tm_v, &bars->v_full[st],
-                      j * kBN + sub * 64, v_row);
+          for (int sub = 0; sub < C::kSubTilesV; ++sub)
+            tma_load_2d(sV + st * C::kTileBytesV + sub * C::kSubBytesV, &tm_v, &bars->v_full[st],
+                        j * kBN + sub * 64, v_row);
+        }
       }
     }
    } else if (is_mma_warp(warp)) {
@@ -722,41 +776,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       };
 
-      mbar_wait(&bars->q_full, 0, err_flag, 201, dead);
+      // Items of this CTA, k = 0, 1, ...: G = global half-step of the item's step 0 (score / P buffers and the phases of
+      // s_full / p_full follow G + i), J0 = global K / V tile of its tile 0 (ring stages and their phases follow J0 + j).
+      int k = 0;
+      for (int it = item0; it < n_items && !dead; it += item_stride, ++k) {
+      constexpr int G = 0;                        // (persistent: n_half % 4 == 0, every item starts in an even phase on buffer 0)
+      const int J0 = kPersist ? k * n_tiles : 0;
+      mbar_wait(&bars->q_full, (uint32_t)k & 1, err_flag, 201, dead);
       tc_fence_after();
       __syncwarp();
       auto qk_step = [&](int in, int wait_site, long long* stamp = nullptr) {   // S_mt(in): wait for its K tile, issue, signal, release
-        const int jn = in >> 1, halfn = in & 1, stn = jn % C::kStagesK;
+        const int jn = J0 + (in >> 1), halfn = in & 1, stn = jn % C::kStagesK;
         mbar_wait(&bars->k_full[stn], (uint32_t)(jn / C::kStagesK) & 1, err_flag, wait_site, dead);
         tc_fence_after();
         if (kTrace && stamp) *stamp = clock64();
-        issue_qk(mt, in & 1, stn, halfn);
-        commit(&bars->s_full[mt][in & 1]);
+        issue_qk(mt, (G + in) & 1, stn, halfn);
+        commit(&bars->s_full[mt][(G + in) & 1]);
         // last read of this K tile by this warp: one arrival per MMA warp frees the stage
         if (!kSoftRing && (kStride == 2 || halfn == 1 || in == n_half - 1)) commit(&bars->k_empty[stn]);
       };
       for (int in = 0; in < 3 && in < n_half; ++in) {
         if (!owns(in - 3)) continue;
         if (in == 2) {  // buffer 0 is reusable once the softmax warps hold S(0) in registers
-          mbar_wait(&bars->s0_read[mt], 0, err_flag, 208, dead);
+          mbar_wait(&bars->s0_read[mt], (uint32_t)k & 1, err_flag, 208, dead);
           tc_fence_after();
         }
         qk_step(in, 202);
       }
       if (first + 3 >= n_half) commit(&bars->qk_done);  // this warp issues no further Q·K^T
       for (int i = first; i < n_half; i += kStride) {
-        const int j = i >> 1, half = i & 1;
+        const int j = J0 + (i >> 1), half = i & 1;
         const int st = j % C::kStagesV;
         long long* trm = kTrace ? prm.trace + (size_t)8 * n_half * 4 + (size_t)i * 4 : nullptr;
         const bool tracer = traced_cta && lane == 0 && mt == 0;
         if constexpr (kMmaSplit == 4) refill(j);   // only warps 8 / 10 do anything here (even i)
         mbar_wait(&bars->v_full[st], (uint32_t)(j / C::kStagesV) & 1, err_flag, 203, dead);
-        mbar_wait(&bars->p_full[mt][half], (uint32_t)(i >> 1) & 1, err_flag, 204, dead);
+        mbar_wait(&bars->p_full[mt][(G + i) & 1], (uint32_t)((G + i) >> 1) & 1, err_flag, 204, dead);
         if (kStride == 2 && i > 0)  // the other warp's P·V(i-1) must have retired before O is touched again
           mbar_wait(&bars->pv_done[mt][(i - 1) & 1], (uint32_t)((i - 1) >> 1) & 1, err_flag, 209, dead);
         tc_fence_after();
         if (tracer) trm[0] = clock64();
-        issue_pv(mt, (i + 1) & 1, st, half, i > 0);
+        issue_pv(mt, (G + i + 1) & 1, st, half, i > 0);
         if (!kLazyPv || i + 3 >= n_half) commit(&bars->pv_done[mt][half]);   // no Q.K^T behind the last three
         if (i == n_half - 1) commit(&bars->o_final[mt]);
         if (!kSoftRing && (kStride == 2 || half == 1 || i == n_half - 1)) commit(&bars->v_empty[st]);
@@ -766,6 +826,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (i + 3 + kStride >= n_half) commit(&bars->qk_done);  // that was this warp's last Q·K^T
         }
         if (tracer) trm[3] = clock64();
+      }
       }
     }
    }
@@ -781,14 +842,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tP = prm.debug_no_mma ? tO : tS;
 
     static_assert(!kBlk || kInt8, "block scales only exist for the INT8 variant");
+    // Persistent kernel: the host only selects it when n_half % 4 == 0 (N a multiple of 256), so every item starts on
+    // score buffer 0 with the s_full / p_full barriers in an even phase — the softmax warps need no global step counter
+    // (G = 0) and keep a single extra live value across the loop, the item number k.
+    float pre_c = 1.f, pre_os = 1.f;   // persistent block mode: the next item's row-block scale and V scale, fetched early
+    for (int k = 0;; ++k) {
+    if (item0 + k * item_stride >= n_items) break;
+    if (kPersist && k > 0) set_item(item0 + k * item_stride);
+    constexpr int G = 0, J0 = 0;
+    float4* blk_tab = blk_tab0 + ((kPersist && (k & 1)) ? prm.n_pad / 32 : 0);   // persistent: two tables, alternating
     float c = prm.scale_log2;  // log2(e) / sqrt(d)
     float out_scale = 1.0f;
     const int nblk = prm.n_pad / 32;
+    // fills `tab` with the block constants of `unit_x` and returns {sQ of this row's block in item (unit_x, qb_x), sV_max}
+    auto fetch_item_consts = [&](int unit_x, int qb_x, float4* tab, float& c_x, float& os_x) {
+      const int qblk = (qb_x + t * kBM + row_in_tile) >> 5;
+      c_x = __ldg(prm.blk_scales + (size_t)unit_x * nblk + qblk);
+      os_x = __ldg(prm.blk_vmax + unit_x);
+      const float* gk = prm.blk_scales + ((size_t)prm.units + unit_x) * nblk;
+      const float2* ga = reinterpret_cast<const float2*>(prm.blk_aux) + (size_t)unit_x * nblk;
+      for (int g = threadIdx.x; g < nblk; g += 256) {
+        const float2 a = __ldg(ga + g);
+        tab[g] = make_float4(__ldg(gk + g), a.x, a.y, 0.f);
+      }
+    };
     if constexpr (kBlk) {
-      // c = log2e/sqrt(d) * sQ of this row's 32-row block; the K/V block factors come per step
-      const int qblk = (q_base + t * kBM + row_in_tile) >> 5;
-      c *= __ldg(prm.blk_scales + (size_t)unit * nblk + qblk);
-      out_scale = __ldg(prm.blk_vmax + unit);
+      // c = log2e/sqrt(d) * sQ of this row's 32-row block; the K/V block factors come per step.  The per-32-key-block
+      // constants {sK, log2 r, 1/r, -} of the unit are staged in shared memory (256 softmax threads), so the per-step
+      // lookups are two broadcast LDS.128.  Persistent kernel: items after the first find all of it fetched by the
+      // previous item, under its wait for the last P.V.
+      if (kPersist && k > 0) {
+        c *= pre_c;
+        out_scale = pre_os;
+      } else {
+        float cq;
+        fetch_item_consts(unit, q_base, blk_tab, cq, out_scale);
+        c *= cq;
+      }
     } else if constexpr (kInt8) {
       const float sq = prm.scales[unit];
       const float sk = prm.scales[prm.units + unit];
@@ -807,16 +897,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     long long* tr = kTrace ? prm.trace + (size_t)warp * n_half * 4 : nullptr;
     if (tracer && warp == 0) phase[1] = clock64();
 
-    // block mode: per-32-key-block constants {sK, log2 r, 1/r, -} of this unit staged in shared memory
-    // once per CTA (256 softmax threads), so the per-step lookups are two broadcast LDS.128.
-    if constexpr (kBlk) {
-      const float* gk = prm.blk_scales + ((size_t)prm.units + unit) * nblk;
-      const float2* ga = reinterpret_cast<const float2*>(prm.blk_aux) + (size_t)unit * nblk;
-      for (int g = threadIdx.x; g < nblk; g += 256) {
-        const float2 a = __ldg(ga + g);
-        blk_tab[g] = make_float4(__ldg(gk + g), a.x, a.y, 0.f);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+    if constexpr (kBlk && !kPersist) asm volatile("bar.sync 1, 256;" ::: "memory");
+    if constexpr (kPersist) {
+      // one rendezvous of the 256 softmax threads per item: it orders the table fill (the other table may still be in use
+      // by warps that are finishing the previous item) and makes the decision to drain after a failure uniform
+      uint32_t any_dead;
+      asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(any_dead) : "r"((uint32_t)dead) : "memory");
+      if (any_dead) break;
     }
 
     // The softmax loop is software-pipelined over half-steps.  While the exponentials of step i
@@ -868,24 +956,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const bool releaser = kSoftRing && (threadIdx.x & 127) == 0;
     auto on_scores = [&](int r) {
       if (!kSoftRing || !releaser) return;
-      if (r & 1) mbar_arrive(&bars->k_empty[(r >> 1) % C::kStagesK]);              // K tile r/2: both halves read
-      else if (r >= 4) mbar_arrive(&bars->v_empty[((r - 4) >> 1) % C::kStagesV]);   // P.V(r-3) retired: V tile (r-4)/2
+      if (r & 1) mbar_arrive(&bars->k_empty[(J0 + (r >> 1)) % C::kStagesK]);              // K tile r/2: both halves read
+      else if (r >= 4) mbar_arrive(&bars->v_empty[(J0 + ((r - 4) >> 1)) % C::kStagesV]);   // P.V(r-3) retired: V tile (r-4)/2
     };
     // "P.V(j) has retired": s_full(j+3) when that Q.K^T exists, the step's own pv_done commit otherwise
     const int pv_c0 = n_half > 3 ? n_half - 3 : 0;   // first half-step with a pv_done commit (kLazyPv)
+    // pv_done[b] completes once per committed step of local parity b: the last three half-steps of every item, i.e.
+    // twice per item for the parity of step n_half - 1 and once for the other
+    auto pv_base = [&](int par) { return kPersist ? k * ((par == ((n_half - 1) & 1)) ? 2 : 1) : 0; };
     auto wait_pv = [&](int j, int site) {
       if (kLazyPv && j + 3 < n_half)
-        mbar_wait(&bars->s_full[t][(j + 3) & 1], (uint32_t)((j + 3) >> 1) & 1, err_flag, site, dead);
+        mbar_wait(&bars->s_full[t][(G + j + 3) & 1], (uint32_t)((G + j + 3) >> 1) & 1, err_flag, site, dead);
       else
-        mbar_wait(&bars->pv_done[t][j & 1], (uint32_t)((kLazyPv ? j - pv_c0 : j) >> 1) & 1, err_flag, site, dead);
+        mbar_wait(&bars->pv_done[t][j & 1], (uint32_t)(pv_base(j & 1) + ((kLazyPv ? j - pv_c0 : j) >> 1)) & 1, err_flag, site, dead);
       tc_fence_after();
     };
     auto probe = [&](int i) {
-      return mbar_test_wait(&bars->s_full[t][i & 1], (uint32_t)(i >> 1) & 1) != 0;
+      return mbar_test_wait(&bars->s_full[t][(G + i) & 1], (uint32_t)((G + i) >> 1) & 1) != 0;
     };
     auto fetch = [&](int i, uint32_t (&dst)[kHN], bool probed = false) {
-      const int buf = i & 1;
-      if (!probed) mbar_wait(&bars->s_full[t][buf], (uint32_t)(i >> 1) & 1, err_flag, 301 + t, dead);
+      const int buf = (G + i) & 1;
+      if (!probed) mbar_wait(&bars->s_full[t][buf], (uint32_t)((G + i) >> 1) & 1, err_flag, 301 + t, dead);
       tc_fence_after();
       on_scores(i);
       tmem_ld32(tS + buf * kHN, &dst[0]);
@@ -905,10 +996,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     };
     auto publish = [&](int i, const uint32_t (&p)[kHN / 2]) {
-      store_p(tP + ((i + 1) & 1) * kHN, p);
+      store_p(tP + ((G + i + 1) & 1) * kHN, p);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->p_full[t][i & 1]);
+      mbar_arrive(&bars->p_full[t][(G + i) & 1]);
       if (tracer) tr[i * 4 + 3] = clock64();
     };
     // Raise the reference max for step i (and, for i > 0, rescale l and the O rows in TMEM).
@@ -972,18 +1063,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr int kA1 = kFa + 3, kA2 = kFa + 9;
       static_assert(kA2 < kFb && kFb < kHN / 2, "split points out of order");
       exps(Range<0, kFa>{}, cur, p, kc, ls);
-      if (!published) store_p(tP + (i & 1) * kHN, p_prev);  // P(i-1) over the S(i) buffer
+      if (!published) store_p(tP + ((G + i) & 1) * kHN, p_prev);  // P(i-1) over the S(i) buffer
       exps(Range<kFa, kA1>{}, cur, p, kc, ls);
       if (!published) {
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bars->p_full[t][(i - 1) & 1]);
+        mbar_arrive(&bars->p_full[t][(G + i - 1) & 1]);
         if (tracer) tr[(i - 1) * 4 + 3] = clock64();
       }
       if constexpr (kPrefetch) {
         if (tracer) tr[i * 4 + 1] = clock64();
-        const int buf = (i + 1) & 1;
-        if (!s_ready) mbar_wait(&bars->s_full[t][buf], (uint32_t)((i + 1) >> 1) & 1, err_flag, 301 + t, dead);
+        const int buf = (G + i + 1) & 1;
+        if (!s_ready) mbar_wait(&bars->s_full[t][buf], (uint32_t)((G + i + 1) >> 1) & 1, err_flag, 301 + t, dead);
         tc_fence_after();
         on_scores(i + 1);
         tmem_ld32(tS + buf * kHN, &nxt[0]);
@@ -1078,6 +1169,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     unpack2(lsum[1], lc, ld);
     l = kBlk ? l_acc : (la + lb) + (lc + ld);
     const float inv = (l > 0.f) ? out_scale / l : 0.f;  // fa_tc_int8_b.cu:549-553 guard
+    if constexpr (kPersist) {   // (unit, q_base) are recomputed here instead of being kept live across the main loop
+      int kk = k;
+      asm volatile("" : "+r"(kk));
+      if constexpr (kBlk) {     // the next item's constants go into the other table (its last readers finished an item ago)
+        const int itn = item0 + (kk + 1) * item_stride;
+        if (itn < n_items)
+          fetch_item_consts(itn / nqb, (itn % nqb) * (2 * kBM), blk_tab0 + ((kk & 1) ? 0 : prm.n_pad / 32), pre_c, pre_os);
+      }
+      set_item(item0 + kk * item_stride);
+    }
     const int row = q_base + t * kBM + row_in_tile;
     const int b = unit / prm.H, head = unit % prm.H;
     const int osz = prm.out_dtype == 0 ? 4 : 2;   // output element size
@@ -1091,7 +1192,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     constexpr bool kStaged = C::kTileBytesQK >= 16384;
     constexpr bool kTmaStore = C::kStagesK * C::kTileBytesQK >= 65536;
     // (a parity wait on pv_done could alias here: the barrier may be two phases behind)
-    mbar_wait(&bars->o_final[t], 0, err_flag, 321 + t, dead);
+    mbar_wait(&bars->o_final[t], (uint32_t)k & 1, err_flag, 321 + t, dead);
     dead = __any_sync(0xffffffffu, dead);
     tc_fence_after();
     if (tracer && warp == 0) phase[4] = clock64();
@@ -1102,18 +1203,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // lane hands them to the TMA as tensor stores; rows beyond N are clipped by the tensor map
     // ([B][N][H*d], box 1 x 32 x 32).  All TMEM loads are issued up front, one proxy fence per two tiles.
     if (kTmaStore && prm.tma_store) {
-      mbar_wait(&bars->qk_done, 0, err_flag, 341 + t, dead);
+      if constexpr (!kPersist) mbar_wait(&bars->qk_done, 0, err_flag, 341 + t, dead);
       // The TMA needs ~1.2 k clk to read a staged tile, so re-using a staging tile costs that much.
       // When the K and V rings together give every warp 16 KB, all (up to four) tiles of a warp are
       // staged at once; the V ring is only free once the other query tile has finished as well.
+      // Persistent kernel: only the V^T ring is used (the K ring already receives the next item's tiles).
       constexpr int kRingBytes = C::kStagesK * C::kTileBytesQK + C::kStagesV * C::kTileBytesV;
       constexpr int kChunks = kD / 32;
-      constexpr int kBufs = (kRingBytes >= 8 * 4 * 4096 && kChunks > 2) ? 4 : 2;
-      if constexpr (kBufs == 4) {
-        mbar_wait(&bars->o_final[t ^ 1], 0, err_flag, 343 + t, dead);
+      constexpr int kBufsV = (C::kStagesV * C::kTileBytesV) / (8 * 4096);
+      static_assert(!kPersist || kBufsV >= 2, "persistent kernel: the V^T ring must give every softmax warp two staging tiles");
+      constexpr int kBufs = kPersist ? (kBufsV < kChunks ? kBufsV : kChunks)
+                                     : ((kRingBytes >= 8 * 4 * 4096 && kChunks > 2) ? 4 : 2);
+      if constexpr (kBufs == 4 || kPersist) {
+        mbar_wait(&bars->o_final[t ^ 1], (uint32_t)k & 1, err_flag, 343 + t, dead);
         tc_fence_after();
       }
-      float* stage = reinterpret_cast<float*>(sK) + warp * (kBufs * 1024);   // kBufs x (32 rows x 32 floats)
+      float* stage = reinterpret_cast<float*>(kPersist ? sV : sK) + warp * (kBufs * 1024);   // kBufs x (32 rows x 32 floats)
       const int row0 = q_base + t * kBM + (warp & 3) * 32;
       // Rolled on purpose: this code runs once per CTA, straight out of a cold instruction cache, and
       // its fetch — not its execution — is what it costs.
@@ -1156,7 +1261,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       if (tracer && warp == 0) phase[11] = clock64();
-      if (lane == 0) bulk_wait_group_read<0>();
+      if (lane == 0) {
+        bulk_wait_group_read<0>();
+        if constexpr (kPersist) mbar_arrive(&bars->epi_done);   // this warp's staging tiles may be overwritten (V^T producer)
+      }
       __syncwarp();
     } else if (kStaged && vec_ok && prm.out_dtype == 0) {
       // Same staging through the (dead) Q tile of this warpgroup, written out with ordinary 16-byte
@@ -1240,6 +1348,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
        }
       }
     }
+    }   // items
   }
 
   // ---------------------------------------------------------------------------- teardown
@@ -1254,7 +1363,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (prm.cycles != nullptr && threadIdx.x == 0) {   // development aid: SM clocks this CTA was resident
     const long long t_exit = clock64();
     atomicAdd(prm.cycles, (unsigned long long)(t_exit - t_entry));
-    atomicAdd(prm.cycles + 1, 1ull);
+    atomicAdd(prm.cycles + 1, kPersist ? (unsigned long long)((n_items - item0 + item_stride - 1) / item_stride) : 1ull);   // work items
     // per SM: {~(earliest CTA start), latest CTA end} -> span of the launch on that SM against the sum of residencies
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1332,8 +1441,24 @@ bool make_map_3d_out(CUtensorMap* m, const void* base, int out_dtype, uint64_t d
   return true;
 }
 
+// Can this launch run on the persistent kernel?  It needs the TMA-store epilogue (staging in the V^T ring), at least four
+// half-steps per item and room for the second block-scale table.
+template <bool kInt8, int kD, bool kPv8>
+bool persistent_ok(const AttnLaunch& a) {
+  using C = Cfg<kInt8, kD, kPv8>;
+  const char* e = getenv("QMHA_PERSIST");   // read per launch (tests switch it inside one process)
+  const int mode = e && *e ? atoi(e) : QMHA_DEFAULT_PERSIST;
+  if (!mode || a.trace) return false;
+  const uint64_t o_ld = a.o_ld > 0 ? (uint64_t)a.o_ld : (uint64_t)a.H * a.d, o_elt = a.out_dtype == 0 ? 4 : 2;
+  const uint64_t o_bs = a.o_bs > 0 ? (uint64_t)a.o_bs : (uint64_t)a.N * o_ld;
+  if ((a.d % 32) != 0 || (o_ld * o_elt) % 16 != 0 || (o_bs * o_elt) % 16 != 0 || getenv("QMHA_NO_TMA_STORE") != nullptr) return false;
+  if ((a.N + kHN - 1) / kHN < 4 || (a.N % 256) != 0) return false;   // every item must start on score buffer 0, phase 0
+  const size_t smem = (size_t)C::kSmemBytes + (a.blk_scales ? (size_t)(a.n_pad / 32) * 32 : 0);
+  return smem <= 227 * 1024;
+}
+
 template <bool kInt8, int kD, int kPolyEvery, bool kBlk, bool kTrace, int kFa = 6, int kFb = 25, bool kBf16 = false,
-          bool kPv8 = false>
+          bool kPv8 = false, bool kPersist = false>
 bool launch_cfg(const AttnLaunch& a, std::string* err) {
   using C = Cfg<kInt8, kD, kPv8>;
   const uint64_t units = (uint64_t)a.B * a.H;
@@ -1363,9 +1488,9 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
                            o_ld, o_bs, 32, 32, err))
         return false;
   }
-  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb, kBf16, kPv8>;
-  // block mode keeps one float4 of constants per 32-key block of the unit behind the barriers
-  const size_t smem_bytes = (size_t)C::kSmemBytes + (kBlk ? (size_t)(a.n_pad / 32) * 16 : 0);
+  auto kern = attn_fwd_kernel<kInt8, kD, kPolyEvery, kBlk, kTrace, kFa, kFb, kBf16, kPv8, kPersist>;
+  // block mode keeps one float4 of constants per 32-key block of the unit behind the barriers (persistent: two tables)
+  const size_t smem_bytes = (size_t)C::kSmemBytes + (kBlk ? (size_t)(a.n_pad / 32) * 16 * (kPersist ? 2 : 1) : 0);
   if (smem_bytes > 227 * 1024) {
     *err = "sequence too long for the per-block scale table in shared memory (use head granularity)";
     return false;
@@ -1401,6 +1526,18 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.n_peers = a.n_peers;
   for (int pe = 0; pe < kMaxPeers; ++pe) p.peer_O[pe] = pe < a.n_peers ? a.peer_O[pe] : nullptr;
   dim3 grid((a.N + 2 * kBM - 1) / (2 * kBM), (unsigned)units, 1);
+  p.n_qblocks = (int)grid.x;
+  p.n_items = (int)(grid.x * units);
+  if constexpr (kPersist) {
+    static int n_sm[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && n_sm[dev] == 0) cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    const char* ge = getenv("QMHA_PERSIST_GRID");   // tuning aid: CTAs of the persistent grid (default: one per SM)
+    const int grid_env = ge && *ge ? atoi(ge) : 0;
+    const int sms = grid_env > 0 ? grid_env : ((dev >= 0 && dev < 64 && n_sm[dev] > 0) ? n_sm[dev] : 148);
+    grid = dim3((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
+  }
   kern<<<grid, kThreads, smem_bytes, a.stream>>>(tq, tk, tv, to, peers, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("attention launch: ") + cudaGetErrorString(e); return false; }
@@ -1469,12 +1606,16 @@ bool launch_attention(const AttnLaunch& a, std::string* err) {
       case 128: QMHA_DISPATCH_PV8(false, 128) break;
     }
   } else if (a.int8 && blk) {
+    if (a.d_pad == 128 && poly == 0 && persistent_ok<true, 128, false>(a))
+      return launch_cfg<true, 128, 0, true, false, QMHA_FA, QMHA_FB, false, false, true>(a, err);
     switch (a.d_pad) {
       case 32: QMHA_DISPATCH(true, true, 32, false) break;
       case 64: QMHA_DISPATCH(true, true, 64, false) break;
       case 128: QMHA_DISPATCH(true, true, 128, false) break;
     }
   } else if (a.int8) {
+    if (a.d_pad == 128 && poly == 0 && persistent_ok<true, 128, false>(a))
+      return launch_cfg<true, 128, 0, false, false, QMHA_FA, QMHA_FB, false, false, true>(a, err);
     switch (a.d_pad) {
       case 32: QMHA_DISPATCH(true, false, 32, false) break;
       case 64: QMHA_DISPATCH(true, false, 64, false) break;

@@ -32,6 +32,8 @@ struct AttnParams {
   int one;              // 1 (a value the compiler cannot fold; see i2f_magic)
   unsigned long long* cycles;  // development aid: {sum of CTA residency clocks, CTA count} or nullptr
   long long o_ld, o_bs; // distance between consecutive rows / batch entries of O in elements (dense: H*d, N*H*d)
+  int n_qblocks;        // 256-row query blocks per unit
+  int n_items;          // work items (unit, query block) of the launch: n_qblocks * units (persistent kernel)
   int n_peers;          // further destinations that receive the same bytes (replicas on NVLink peers)
   void* peer_O[kMaxPeers];
 };

@@ -169,3 +169,36 @@ def test_replica_on_a_second_gpu_in_one_process(torch, qm):
         assert torch.equal(local_wide[:, :, :heads * d], dense)
         assert torch.equal(remote[:, :, :heads * d].cpu(), dense.cpu())
         assert bool((remote[:, :, heads * d:] == -1.0).all())
+
+
+@pytest.mark.parametrize("gran", ["block", "head"])
+def test_persistent_kernel_is_bit_identical(torch, qm, gran, monkeypatch):
+    """QMHA_PERSIST=1 (opt-in): one CTA per SM walks the (unit, query block) items with the barriers, TMEM and
+    constant tiles kept alive, the next item's Q / K tiles prefetched under the previous item's output stores.
+    256 items on 148 SMs, so CTAs process one or two items; also with a strided slab + replica as output."""
+    B, N, H, d = 2, 4096, 8, 128
+    q, k, v = _inputs(torch, B, N, H * d, seed=21)
+    g = qm.GRAN_BLOCK if gran == "block" else qm.GRAN_HEAD
+    monkeypatch.setenv("QMHA_PERSIST", "0")
+    ref = qm.forward(q, k, v, H, kernel="int8", gran=g)
+    _sync(torch, qm)
+    monkeypatch.setenv("QMHA_PERSIST", "1")
+    launches = qm.launch_count()
+    out = qm.forward(q, k, v, H, kernel="int8", gran=g)
+    _sync(torch, qm)
+    assert qm.launch_count() > launches
+    assert torch.equal(out, ref)
+    big = torch.zeros((B, N + 3, 2 * H * d), device="cuda")
+    peer = torch.zeros_like(big)
+    qm.forward(q, k, v, H, kernel="int8", gran=g, out=big[:, :N, H * d:], peer_outs=[peer[:, :N, H * d:]])
+    _sync(torch, qm)
+    assert torch.equal(big[:, :N, H * d:], ref) and torch.equal(peer, big)
+    for grid in ("1", "37"):                      # many items per CTA
+        monkeypatch.setenv("QMHA_PERSIST_GRID", grid)
+        small = qm.forward(q[:1, :1024], k[:1, :1024], v[:1, :1024], H, kernel="int8", gran=g)
+        _sync(torch, qm)
+        monkeypatch.setenv("QMHA_PERSIST", "0")
+        small_ref = qm.forward(q[:1, :1024], k[:1, :1024], v[:1, :1024], H, kernel="int8", gran=g)
+        _sync(torch, qm)
+        monkeypatch.setenv("QMHA_PERSIST", "1")
+        assert torch.equal(small, small_ref)
