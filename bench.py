@@ -464,6 +464,63 @@ def run_native(args):
                       "parity": c5_par}
         del j5
 
+    # ---- fused gather (N > 1): C4 (B = 8 in total) split over the ranks, the 1.07 GB fp32 result replicated on every rank.
+    # Not the headline path (the north star keeps collectives off it): it shows the compute -> all-gather pair as ONE kernel —
+    # the attention epilogue TMA-stores every finished tile into all replicas over NVLink (qmha_args.peer_O, CUDA IPC) —
+    # beside the same computation followed by an NCCL all-gather, and checks that both give the same bits.
+    fused = None
+    if world > 1 and args.workload == "c4" and not args.no_fused_gather and B % world == 0:
+        try:
+            torch.cuda.empty_cache()
+            from quantizedmha_b200.sharding import ReplicatedOutput
+            lo, hi = unit_range(B, world, rank)
+            gen = torch.Generator(device=dev).manual_seed(7700 + rank)
+            fq, fk, fv = (torch.rand((hi - lo, N, dm), device=dev, generator=gen) for _ in range(3))
+            rep = ReplicatedOutput(B, N, H, d, dtype=torch.float32, device=dev)
+            off = lo * N * dm * 4
+            peers = [rep.peer_base[r] + off for r in sorted(rep.peer_base)]
+            own = torch.empty_like(fq)
+            gathered = torch.empty((B, N, dm), device=dev)
+
+            def timed(fn, reps=5):
+                fn(); fn()
+                torch.cuda.synchronize(); barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return max_over_ranks([e0.elapsed_time(e1) / reps])[0]
+
+            def f_compute():
+                qm.forward(fq, fk, fv, H, kernel=kernel, gran=gran, out=own)
+
+            def f_nccl():
+                qm.forward(fq, fk, fv, H, kernel=kernel, gran=gran, out=own)
+                dist.all_gather_into_tensor(gathered, own)
+
+            def f_fused():
+                rep.fence()
+                qm.forward(fq, fk, fv, H, kernel=kernel, gran=gran, out=rep.local[lo:hi], peer_outs=peers)
+                rep.fence()
+
+            t_c, t_n, t_f = timed(f_compute), timed(f_nccl), timed(f_fused)
+            torch.cuda.synchronize()
+            qm.binding.check_async_error()
+            same = bool(torch.equal(rep.local, gathered))
+            flag = torch.tensor([1 if same else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            fused = {"workload": f"c4 split over {world} GPUs (B={B} in total), fp32 result replicated on every rank",
+                     "replicated_bytes": B * N * dm * 4, "ms_own_slabs_only": t_c, "ms_compute_then_nccl_all_gather": t_n,
+                     "ms_fused_epilogue_stores": t_f, "replicas_equal_nccl_result_on_every_rank": bool(int(flag.item())),
+                     "api": "qmha_forward_ex with peer_O (TMA stores into CUDA-IPC mapped peer tensors) between two 4-byte NCCL fences"}
+            barrier()
+            rep.close()
+            del rep, own, gathered, fq, fk, fv
+        except Exception as e:  # noqa: BLE001  (an optional section must never take the bench line down)
+            fused = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     flops_rank = 4.0 * Bl * H * N * N * d
     flops_all = 4.0 * (B if scaling == "strong" else B * world) * H * N * N * d
     E = Bl * N * dm
@@ -557,6 +614,8 @@ def run_native(args):
     }
     if scaling_c5 is not None:
         line["scaling_c5"] = scaling_c5
+    if fused is not None:
+        line["fused_gather"] = fused
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
@@ -586,6 +645,7 @@ def main():
     ap.add_argument("--no-pv8", action="store_true", help="skip the extra timing of the opt-in INT8 P.V mode")
     ap.add_argument("--no-e2e16", action="store_true", help="skip the fp16-host-buffer variant of the e2e measurement")
     ap.add_argument("--no-c5", action="store_true", help="N>1: skip the C5 strong-scaling measurement")
+    ap.add_argument("--no-fused-gather", action="store_true", help="N>1: skip the fused-gather (peer-memory epilogue) measurement")
     ap.add_argument("--scales", default="block", choices=["head", "block", "tensor"],
                     help="granularity of the dynamic INT8 scales (block = the reference's 32-row tiles)")
     args = ap.parse_args()
