@@ -217,10 +217,12 @@ int qmha_get_rope(void);
  *                    works when the allocator does not use expandable segments); handle = 64 opaque bytes,
  *                    *offset = distance of dev_ptr from the allocation's base.
  *   qmha_ipc_open:   maps the allocation on the CURRENT device of the calling process and returns base + offset;
- *                    the mapping is cached per handle and released by qmha_ipc_close_all() / qmha_shutdown().
+ *                    mappings are cached per handle and reference-counted: qmha_ipc_close(ptr) drops one reference
+ *                    (the mapping goes with the last one), qmha_ipc_close_all() / qmha_shutdown() release everything.
  * Several devices in ONE process need no handles: qmha_enable_peer_access(dev, peer) once per ordered pair. */
 int qmha_ipc_export(const void* dev_ptr, unsigned char handle[64], int64_t* offset);
 int qmha_ipc_open(const unsigned char handle[64], int64_t offset, void** dev_ptr);
+int qmha_ipc_close(void* dev_ptr);
 int qmha_ipc_close_all(void);
 int qmha_enable_peer_access(int dev, int peer);
 

@@ -75,6 +75,8 @@ def declare(L: C.CDLL) -> C.CDLL:
         L.qmha_ipc_export.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
         L.qmha_ipc_open.argtypes = [C.c_char_p, C.c_int64, C.POINTER(vp)]
         L.qmha_ipc_close_all.argtypes = []
+        if hasattr(L, "qmha_ipc_close"):
+            L.qmha_ipc_close.argtypes = [vp]
         L.qmha_enable_peer_access.argtypes = [i, i]
     L.qmha_launch_count.restype = C.c_int64
     L.qmha_version.restype = C.c_char_p
@@ -253,6 +255,11 @@ def ipc_open(handle: bytes, offset: int) -> int:
     p = C.c_void_p()
     _check(lib().qmha_ipc_open(C.create_string_buffer(handle, 64), offset, C.byref(p)))
     return int(p.value)
+
+
+def ipc_close(addr: int) -> None:
+    """Drops one reference to the mapping behind an address returned by ipc_open."""
+    _check(lib().qmha_ipc_close(addr))
 
 
 def ipc_close_all() -> None:

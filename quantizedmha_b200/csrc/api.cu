@@ -906,7 +906,7 @@ int qmha_forward_host_ex(const void* Qv, const void* Kv, const void* Vv, void* O
 
 // ---- peer memory: CUDA IPC mappings of other ranks' output tensors (qmha_args.peer_O) ----------------------
 namespace {
-struct IpcMapping { int dev; void* base; };
+struct IpcMapping { int dev; void* base; size_t size; int refs; };
 std::map<std::string, IpcMapping> g_ipc;   // key: device number + the 64 handle bytes
 typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
 GetAddressRangeFn get_address_range_fn() {
@@ -968,11 +968,36 @@ int qmha_ipc_open(const unsigned char handle[64], int64_t offset, void** dev_ptr
     void* base = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) { cudaGetLastError(); return fail_cuda("cudaIpcOpenMemHandle", e); }
-    it = g_ipc.emplace(key, IpcMapping{dev, base}).first;
+    size_t size = 0;
+    CUdeviceptr b0 = 0;
+    GetAddressRangeFn range = get_address_range_fn();
+    if (range) range(&b0, &size, (CUdeviceptr)(uintptr_t)base);
+    it = g_ipc.emplace(key, IpcMapping{dev, base, size, 0}).first;
   }
+  it->second.refs += 1;
   *dev_ptr = static_cast<char*>(it->second.base) + offset;
   g_err.clear();
   return 0;
+}
+
+int qmha_ipc_close(void* dev_ptr) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto it = g_ipc.begin(); it != g_ipc.end(); ++it) {
+    IpcMapping& m = it->second;
+    const char* b = static_cast<const char*>(m.base);
+    const char* p = static_cast<const char*>(dev_ptr);
+    if (p < b || (m.size ? p >= b + m.size : p != b)) continue;
+    if (--m.refs > 0) return 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(m.dev);
+    const cudaError_t e = cudaIpcCloseMemHandle(m.base);
+    cudaSetDevice(cur);
+    g_ipc.erase(it);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail_cuda("cudaIpcCloseMemHandle", e); }
+    return 0;
+  }
+  return fail("qmha_ipc_close: not a pointer returned by qmha_ipc_open");
 }
 
 int qmha_ipc_close_all(void) {

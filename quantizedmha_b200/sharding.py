@@ -192,12 +192,13 @@ class ReplicatedOutput:
         the ranks enqueued before it — kernels that write into the replicas, kernels that read them — is complete
         on every rank before anything enqueued after it starts."""
         import torch.distributed as dist
-        dist.all_reduce(self._fence, group=self.group)
+        dist.all_reduce(self._fence, op=dist.ReduceOp.MAX, group=self.group)   # (zeros stay zeros: nothing to overflow)
 
     def close(self):
         from . import binding as qb
+        for addr in self.peer_base.values():      # only this object's mappings (they are reference-counted per allocation)
+            qb.ipc_close(addr)
         self.peer_base = {}
-        qb.ipc_close_all()
 
 
 def forward_fused_gather(Q, K, V, H: int, rep: "ReplicatedOutput", kernel="int8", gran: int = -1, forward_fn=None,
