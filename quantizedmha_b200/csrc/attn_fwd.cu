@@ -846,7 +846,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // score buffer 0 with the s_full / p_full barriers in an even phase — the softmax warps need no global step counter
     // (G = 0) and keep a single extra live value across the loop, the item number k.
     float pre_c = 1.f, pre_os = 1.f;   // persistent block mode: the next item's row-block scale and V scale, fetched early
-    for (int k = 0;; ++k) {
+#ifndef QMHA_PERSIST_SINGLE
+#define QMHA_PERSIST_SINGLE 0   // code-generation experiment: 1 = the softmax roles stop after their first item (run with QMHA_PERSIST_GRID = items)
+#endif
+    for (int k = 0; k < (QMHA_PERSIST_SINGLE ? 1 : 0x7fffffff); ++k) {
     if (item0 + k * item_stride >= n_items) break;
     if (kPersist && k > 0) set_item(item0 + k * item_stride);
     constexpr int G = 0, J0 = 0;
