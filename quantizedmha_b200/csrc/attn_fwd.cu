@@ -98,8 +98,15 @@ __host__ __device__ constexpr bool is_mma_warp(int warp) {
   return kMmaSplit == 4 ? warp >= 8 : (warp == 8 || warp == 11);
 }
 constexpr int kThreads = 384;            // 2 softmax warpgroups + 1 service warpgroup (MMA, TMA, 2 idle)
-constexpr int kRegsSoftmax = 208;        // setmaxnreg budgets: 2*128*208 + 128*72 = 62464 <= 65536
-constexpr int kRegsService = 72;
+#ifndef QMHA_REGS_SOFTMAX
+#define QMHA_REGS_SOFTMAX 208
+#endif
+#ifndef QMHA_REGS_SERVICE
+#define QMHA_REGS_SERVICE 72
+#endif
+constexpr int kRegsSoftmax = QMHA_REGS_SOFTMAX;        // setmaxnreg budgets: 2*128*208 + 128*72 = 62464 <= 65536
+constexpr int kRegsService = QMHA_REGS_SERVICE;
+static_assert(2 * 128 * kRegsSoftmax + 128 * kRegsService <= 65536 && kRegsSoftmax % 8 == 0 && kRegsService % 8 == 0, "register budgets");
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;  // S_t[b] at kColS_t + 64*b
 constexpr float kRescaleThreshold = 4.0f;  // log2 units: P <= 2^4, well inside fp16
