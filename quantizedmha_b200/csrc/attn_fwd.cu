@@ -82,6 +82,12 @@ static_assert((QMHA_SOFT_RING == 0 && QMHA_LAZY_PV == 0) || kMmaSplit == 2, "wri
 #define QMHA_BIAS_MMA 1
 #endif
 constexpr bool kBiasMma = QMHA_BIAS_MMA != 0;
+// Code-generation experiments on the persistent kernel (run with QMHA_PERSIST_GRID = number of items, i.e. one item per
+// CTA): bit 0 = the softmax warps stop after their first item, bit 1 = the MMA warps, bit 2 = the producers, bit 3 = the
+// epilogue stages through the K + V^T rings like the one-CTA-per-item kernel.
+#ifndef QMHA_PERSIST_SINGLE
+#define QMHA_PERSIST_SINGLE 0
+#endif
 // Persistent INT8 d = 128 kernel (see attn_fwd_kernel, kPersist): 0 = off unless QMHA_PERSIST=1, 1 = on unless QMHA_PERSIST=0.
 // Built, bit-identical, and measured SLOWER than one CTA per item at C4 (187.9 k against 181.0 k clk per item): the gaps
 // between CTAs, the setup and the first-scores latency do disappear (1.6 k clk per item against the same code run with one
@@ -616,7 +622,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ======================================================================== TMA producer: Q, K ring
     if (lane == 0) {  // Q and K tiles 0 .. kStagesK-1 of the first item were requested during the CTA setup
       int k = 0;
-      for (int it = item0; it < n_items && !dead; it += item_stride, ++k) {
+      for (int it = item0; it < n_items && !dead && !((QMHA_PERSIST_SINGLE & 4) && k > 0); it += item_stride, ++k) {
         if (kPersist && k > 0) {
           set_item(it);
           // the Q tiles are dead once every Q.K^T of the previous item has retired
@@ -649,7 +655,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ======================================================================== TMA producer: V^T ring
     if (lane == 0) {
       int k = 0;
-      for (int it = item0; it < n_items && !dead; it += item_stride, ++k) {
+      for (int it = item0; it < n_items && !dead && !((QMHA_PERSIST_SINGLE & 4) && k > 0); it += item_stride, ++k) {
         if (kPersist && k > 0) {
           set_item(it);
           // the previous item's output is staged in this ring: wait until its TMA stores have read the tiles
@@ -786,7 +792,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // Items of this CTA, k = 0, 1, ...: G = global half-step of the item's step 0 (score / P buffers and the phases of
       // s_full / p_full follow G + i), J0 = global K / V tile of its tile 0 (ring stages and their phases follow J0 + j).
       int k = 0;
-      for (int it = item0; it < n_items && !dead; it += item_stride, ++k) {
+      for (int it = item0; it < n_items && !dead && !((QMHA_PERSIST_SINGLE & 2) && k > 0); it += item_stride, ++k) {
       constexpr int G = 0;                        // (persistent: n_half % 4 == 0, every item starts in an even phase on buffer 0)
       const int J0 = kPersist ? k * n_tiles : 0;
       mbar_wait(&bars->q_full, (uint32_t)k & 1, err_flag, 201, dead);
@@ -853,10 +859,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // score buffer 0 with the s_full / p_full barriers in an even phase — the softmax warps need no global step counter
     // (G = 0) and keep a single extra live value across the loop, the item number k.
     float pre_c = 1.f, pre_os = 1.f;   // persistent block mode: the next item's row-block scale and V scale, fetched early
-#ifndef QMHA_PERSIST_SINGLE
-#define QMHA_PERSIST_SINGLE 0   // code-generation experiment: 1 = the softmax roles stop after their first item (run with QMHA_PERSIST_GRID = items)
-#endif
-    for (int k = 0; k < (QMHA_PERSIST_SINGLE ? 1 : 0x7fffffff); ++k) {
+    for (int k = 0; k < ((QMHA_PERSIST_SINGLE & 1) ? 1 : 0x7fffffff); ++k) {
     if (item0 + k * item_stride >= n_items) break;
     if (kPersist && k > 0) set_item(item0 + k * item_stride);
     constexpr int G = 0, J0 = 0;
@@ -1213,7 +1216,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // lane hands them to the TMA as tensor stores; rows beyond N are clipped by the tensor map
     // ([B][N][H*d], box 1 x 32 x 32).  All TMEM loads are issued up front, one proxy fence per two tiles.
     if (kTmaStore && prm.tma_store) {
-      if constexpr (!kPersist) mbar_wait(&bars->qk_done, 0, err_flag, 341 + t, dead);
+      constexpr bool kStageV = kPersist && !(QMHA_PERSIST_SINGLE & 8);   // stage through the V^T ring only
+      if constexpr (!kStageV) mbar_wait(&bars->qk_done, (uint32_t)k & 1, err_flag, 341 + t, dead);
       // The TMA needs ~1.2 k clk to read a staged tile, so re-using a staging tile costs that much.
       // When the K and V rings together give every warp 16 KB, all (up to four) tiles of a warp are
       // staged at once; the V ring is only free once the other query tile has finished as well.
@@ -1222,13 +1226,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr int kChunks = kD / 32;
       constexpr int kBufsV = (C::kStagesV * C::kTileBytesV) / (8 * 4096);
       static_assert(!kPersist || kBufsV >= 2, "persistent kernel: the V^T ring must give every softmax warp two staging tiles");
-      constexpr int kBufs = kPersist ? (kBufsV < kChunks ? kBufsV : kChunks)
-                                     : ((kRingBytes >= 8 * 4 * 4096 && kChunks > 2) ? 4 : 2);
-      if constexpr (kBufs == 4 || kPersist) {
+      constexpr int kBufs = kStageV ? (kBufsV < kChunks ? kBufsV : kChunks)
+                                    : ((kRingBytes >= 8 * 4 * 4096 && kChunks > 2) ? 4 : 2);
+      if constexpr (kBufs == 4 || kStageV) {
         mbar_wait(&bars->o_final[t ^ 1], (uint32_t)k & 1, err_flag, 343 + t, dead);
         tc_fence_after();
       }
-      float* stage = reinterpret_cast<float*>(kPersist ? sV : sK) + warp * (kBufs * 1024);   // kBufs x (32 rows x 32 floats)
+      float* stage = reinterpret_cast<float*>(kStageV ? sV : sK) + warp * (kBufs * 1024);   // kBufs x (32 rows x 32 floats)
       const int row0 = q_base + t * kBM + (warp & 3) * 32;
       // Rolled on purpose: this code runs once per CTA, straight out of a cold instruction cache, and
       // its fetch — not its execution — is what it costs.
