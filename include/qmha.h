@@ -100,6 +100,11 @@ typedef struct qmha_args {
   int64_t o_row_stride, o_batch_stride;
   int n_peers;              /* 0 .. QMHA_MAX_PEERS                                                       */
   void* peer_O[7];
+  /* Input placement: Q, K, V may likewise be slabs of larger tensors (the same pitches for all three, in elements of
+   * in_dtype, multiples of 16 bytes; 0 = dense).  The quantise / convert pass reads them in place — a caller that shards
+   * heads hands over its columns of the full [B, N, H*d] tensors without a copy ("inputs / outputs for a
+   * unit are the strided slices [b, :, h, :]"). */
+  int64_t in_row_stride, in_batch_stride;
 } qmha_args;
 #define QMHA_MAX_PEERS 7
 void qmha_args_init(qmha_args* a);

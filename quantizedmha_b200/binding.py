@@ -32,7 +32,7 @@ class QmhaArgs(C.Structure):
                 ("gran", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("rope", C.c_int),
                 ("rope_base", C.c_float), ("variant", C.c_int), ("stream", C.c_void_p),
                 ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64), ("n_peers", C.c_int),
-                ("peer_O", C.c_void_p * 7)]
+                ("peer_O", C.c_void_p * 7), ("in_row_stride", C.c_int64), ("in_batch_stride", C.c_int64)]
 
 
 MAX_PEERS = 7
@@ -209,8 +209,22 @@ def forward(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=N
     shaped and strided like out (replicas on this or on peer-accessible devices)."""
     torch = _torch()
     _check_inputs(Q, K, V, allow16=True)
-    Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
     B, N, d_model = _shape3(Q)
+    # Q, K, V may be slab views (rows / batch entries strided, last dimension contiguous) with one common pitch and
+    # 16-byte aligned origins: the quantise pass reads them in place; anything else is made contiguous first
+    in_ld = in_bs = 0
+    esz = Q.element_size()
+    try:
+        pitches = {_out_strides(t, B, N, d_model) for t in (Q, K, V)}
+    except QmhaError:
+        pitches = set()
+    if (len(pitches) == 1 and all(t.data_ptr() % 16 == 0 for t in (Q, K, V))
+            and all((p * esz) % 16 == 0 for p in next(iter(pitches)))):
+        in_ld, in_bs = next(iter(pitches))
+        if (in_ld, in_bs) == (d_model, N * d_model):
+            in_ld = in_bs = 0
+    else:
+        Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
     if out is None:
         out = torch.empty(Q.shape, dtype=out_dtype or Q.dtype, device=Q.device)
     ld, bs = _out_strides(out, B, N, d_model)
@@ -236,6 +250,7 @@ def forward(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=N
                 raise QmhaError("peer outputs must have the dtype, shape and strides of out")
             a.peer_O[j] = pz.data_ptr()
     a.n_peers = len(peers)
+    a.in_row_stride, a.in_batch_stride = in_ld, in_bs
     _check(lib().qmha_forward_ex(C.byref(a)))
     return out
 

@@ -325,11 +325,18 @@ RopeOpt rope_from(int rope, float base) {   // -1 = process default
 // The caller holds the call lock of `w` (the rope tables live in the workspace).
 int prepare_impl(Workspace* w, const void* Q, const void* K, const void* V, int in_dtype, int B, int N,
                  int d_model, int h, int kernel, int gran, const RopeOpt& rope, void* Qp, void* Kp, void* Vt,
-                 float* scales, unsigned* amax, cudaStream_t stream) {
+                 float* scales, unsigned* amax, cudaStream_t stream, long long in_ld = 0, long long in_bs = 0) {
   int d, n_pad, d_pad;
   if (check_shape(B, N, d_model, h, &d, &n_pad, &d_pad)) return 1;
   if (!dtype_ok(in_dtype)) return fail("unknown input dtype");
   if (check_aligned16(Q, "Q") || check_aligned16(K, "K") || check_aligned16(V, "V")) return 1;
+  if (in_ld != 0 || in_bs != 0) {   // Q, K, V are slabs of larger tensors (same pitches for all three)
+    const long long isz = in_dtype == QMHA_DTYPE_F32 ? 4 : 2;
+    const long long ld = in_ld > 0 ? in_ld : d_model, bs = in_bs > 0 ? in_bs : (long long)N * ld;
+    if (in_ld < 0 || in_bs < 0 || ld < d_model || bs < (long long)N * ld || ld > 0x7fffffffLL)
+      return fail("input strides: in_row_stride >= d_model and in_batch_stride >= N * in_row_stride expected");
+    if ((ld * isz) % 16 != 0 || (bs * isz) % 16 != 0) return fail("input row / batch strides must be multiples of 16 bytes");
+  }
   if (in_dtype != QMHA_DTYPE_F32 && (d & 3) != 0)
     return fail("16-bit inputs need a head dimension that is a multiple of 4");
   qmha::PrepareArgs a;
@@ -339,6 +346,7 @@ int prepare_impl(Workspace* w, const void* Q, const void* K, const void* V, int 
   a.bf16 = kernel == QMHA_KERNEL_BF16;
   a.v8 = kernel == QMHA_KERNEL_INT8_PV8;
   a.stream = stream;
+  a.in_ld = in_ld; a.in_bs = in_bs;
   if (rope.on) {
     if ((d & 7) != 0) return fail("fused RoPE needs a head dimension that is a multiple of 8");
     if (get_rope_table(w, N, d, rope.base, &a.rope)) return 1;
@@ -472,7 +480,8 @@ int forward_device(const qmha_args& a) {
   WorkspaceUse use;   // orders this call behind earlier work on other streams that uses the workspace
   use.begin(w, std::move(call_lock), s);
   if (prepare_impl(w, a.Q, a.K, a.V, a.in_dtype, a.B, a.N, a.d_model, a.h, a.kernel, a.gran,
-                   rope_from(a.rope, a.rope_base), w->Qp, w->Kp, w->Vt, w->scales, w->amax, s))
+                   rope_from(a.rope, a.rope_base), w->Qp, w->Kp, w->Vt, w->scales, w->amax, s, a.in_row_stride,
+                   a.in_batch_stride))
     return 1;
   OutPlace place;
   place.ld = a.o_row_stride; place.bs = a.o_batch_stride; place.n_peers = a.n_peers;

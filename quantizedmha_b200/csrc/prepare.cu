@@ -129,16 +129,16 @@ template <typename TIn>
 __global__ void __launch_bounds__(kAbsmaxThreads)
 absmax_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
               const TIn* __restrict__ V, unsigned* __restrict__ amax_bits, int N, int H, int d, int d_pad,
-              const float2* __restrict__ rope) {
+              const float2* __restrict__ rope, int ld, size_t bs) {
   extern __shared__ unsigned s_amax[];  // [H]
   const int z = blockIdx.z, b = blockIdx.y;
   const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
-  const int d_model = H * d;
+  const int d_model = H * d;   // logical row width; ld / bs = row / batch pitch of the input in elements
   const int r0 = blockIdx.x * kAbsmaxRows;
   const int r1 = min(N, r0 + kAbsmaxRows);
   for (int i = threadIdx.x; i < H; i += blockDim.x) s_amax[i] = 0u;
   __syncthreads();
-  const TIn* base = X + ((size_t)b * N) * d_model;
+  const TIn* base = X + (size_t)b * bs;
   if (rope != nullptr && z < 2) {
     // Fused RoPE (per-tensor / two-pass path): the maxima must be those of the ROTATED rows.  Slots are laid
     // out per head over the padded head dimension (d_pad/4 lanes per head row, a divisor of 32), so the
@@ -153,7 +153,7 @@ absmax_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
       const TIn* col = base + (size_t)head * d + vec * 4;
       float m = 0.f;
       for (int r = r0; r < r1; ++r) {
-        float4 x = col_ok ? In<TIn>::ld4(col + (size_t)r * d_model) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x = col_ok ? In<TIn>::ld4(col + (size_t)r * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
         x = rope_rotate(x, vec, r, N, d, rope);
         m = absmax4(m, x);
       }
@@ -169,17 +169,17 @@ absmax_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
       for (; r + 8 <= r1; r += 8) {
         float4 x[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = In<TIn>::ld4(col + (size_t)(r + u) * d_model);
+        for (int u = 0; u < 8; ++u) x[u] = In<TIn>::ld4(col + (size_t)(r + u) * ld);
 #pragma unroll
         for (int u = 0; u < 8; ++u) m = absmax4(m, x[u]);
       }
-      for (; r < r1; ++r) m = absmax4(m, In<TIn>::ld4(col + (size_t)r * d_model));
+      for (; r < r1; ++r) m = absmax4(m, In<TIn>::ld4(col + (size_t)r * ld));
       atomicMax(&s_amax[head], __float_as_uint(m));
     }
   } else {
     for (int c = threadIdx.x; c < d_model; c += blockDim.x) {
       float m = 0.f;
-      for (int r = r0; r < r1; ++r) m = fmaxf(m, fabsf(In<TIn>::ld1(base + (size_t)r * d_model + c)));
+      for (int r = r0; r < r1; ++r) m = fmaxf(m, fabsf(In<TIn>::ld1(base + (size_t)r * ld + c)));
       atomicMax(&s_amax[c / d], __float_as_uint(m));
     }
   }
@@ -219,14 +219,14 @@ __global__ void __launch_bounds__(kPrepThreads)   // (a six-CTA register budget 
 prepare_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
                const TIn* __restrict__ V, const float* __restrict__ scales, void* __restrict__ Qp,
                void* __restrict__ Kp, uint16_t* __restrict__ Vt, int N, int H, int d, int n_pad,
-               const float2* __restrict__ rope) {
+               const float2* __restrict__ rope, int ld, size_t bs) {
   constexpr bool kInt8 = kOut == 0 || kOut == 3;   // 3 = int8 codes with an int8 V^T (INT8 P.V mode)
   const int z = blockIdx.z, unit = blockIdx.y;
   const int b = unit / H, head = unit % H;
   const int n0 = blockIdx.x * kPrepRows;
   const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
-  const int d_model = H * d;
-  const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+  const int d_model = ld;      // row pitch of the input in elements (dense: H * d); bs = batch pitch
+  const TIn* src = X + (size_t)b * bs + (size_t)head * d;
   float inv_sc = 1.0f;
   if constexpr (kInt8) inv_sc = 1.0f / scales[(size_t)z * gridDim.y + unit];  // fa_tc_int8_b.cu:106
 
@@ -351,13 +351,13 @@ __global__ void __launch_bounds__(kPrepThreads, kRope ? 3 : QMHA_BLKQ_CTAS)
 block_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
                       const TIn* __restrict__ V, float* __restrict__ scales,
                       int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
-                      int N, int H, int d, int n_pad, const float2* __restrict__ rope) {
+                      int N, int H, int d, int n_pad, const float2* __restrict__ rope, int ld, size_t bs) {
   const int z = blockIdx.z, unit = blockIdx.y;  // (heads-fastest CTA order was measured: no gain)
   const int b = unit / H, head = unit % H;
   const int n0 = blockIdx.x * kBlkRows;
   const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
-  const int d_model = H * d;
-  const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+  const int d_model = ld;      // row pitch of the input in elements (dense: H * d); bs = batch pitch
+  const TIn* src = X + (size_t)b * bs + (size_t)head * d;
 
   constexpr int kVecPerRow = kD / 4;
   constexpr int kRowsPerIter = kPrepThreads / kVecPerRow;  // 8 / 16 / 32 rows per pass
@@ -473,7 +473,7 @@ cudaError_t launch_block_cfg(const PrepareArgs& a) {
                    : (a.rope ? block_quantize_kernel<kD, true, TIn> : block_quantize_kernel<kD, false, TIn>);
   kern<<<grid, kPrepThreads, 0, a.stream>>>(
       reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
-      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
+      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope, a.ld(), a.bs());
   return cudaGetLastError();
 }
 
@@ -561,7 +561,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kFusedThr
 fused_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
                       const TIn* __restrict__ V, float* __restrict__ scales,
                       int8_t* __restrict__ Qp, int8_t* __restrict__ Kp, __half* __restrict__ Vt,
-                      int N, int H, int d, int n_pad, const float2* __restrict__ rope) {
+                      int N, int H, int d, int n_pad, const float2* __restrict__ rope, int ld, size_t bs) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) uint8_t fused_smem[];
@@ -572,8 +572,8 @@ fused_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K,
   const int b = unit / H, head = unit % H;
   const int rank = (int)cluster.block_rank();
   const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
-  const int d_model = H * d;
-  const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+  const int d_model = ld;      // row pitch of the input in elements (dense: H * d); bs = batch pitch
+  const TIn* src = X + (size_t)b * bs + (size_t)head * d;
 
   // rows of this CTA: a multiple of 128 so V tiles never straddle CTAs
   const int rows_per_cta = ((n_pad / 128 + kClusterSize - 1) / kClusterSize) * 128;
@@ -741,7 +741,7 @@ stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, con
                        float* __restrict__ scales, int8_t* __restrict__ Qp, int8_t* __restrict__ Kp,
                        __half* __restrict__ Vt, unsigned* __restrict__ ctl, unsigned* __restrict__ amax,
                        unsigned* __restrict__ done, int N, int H, int d, int n_pad, int units,
-                       const float2* __restrict__ rope) {
+                       const float2* __restrict__ rope, int ld, size_t bs) {
   constexpr int kVecPerRow = kD / 4;
   constexpr int kRowsPerIter = kStreamThreads / kVecPerRow;   // 16 / 32 / 64 rows per pass
   constexpr int kLoads = kStreamRows / kRowsPerIter;           // 8 / 4 / 2 float4 per thread
@@ -755,7 +755,7 @@ stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, con
   const int vec = threadIdx.x % kVecPerRow;
   const int rsub = threadIdx.x / kVecPerRow;
   const bool col_ok = vec * 4 < d;
-  const int d_model = H * d;
+  const int d_model = ld;      // row pitch of the input in elements (dense: H * d); bs = batch pitch
   // Item decode (four divisions by run-time values) and the scale arithmetic are done by ONE thread and broadcast
   // through shared memory: done per thread they were a quarter of the kernel's instructions (ncu).
   auto decode = [&](unsigned item, int* o) {   // o = {slab (-1: nothing to do), tile, quantise?, z, b, head}
@@ -779,7 +779,7 @@ stream_quantize_kernel(const TIn* __restrict__ Q, const TIn* __restrict__ K, con
     const int z = s_dec[par][3], b = s_dec[par][4], head = s_dec[par][5];
     const int unit = slab - z * units;
     const TIn* X = z == 0 ? Q : (z == 1 ? K : V);
-    const TIn* src = X + ((size_t)b * N) * d_model + (size_t)head * d;
+    const TIn* src = X + (size_t)b * bs + (size_t)head * d;
     const int n0 = t * kStreamRows;
     float4 x[kLoads];
 #pragma unroll
@@ -871,7 +871,7 @@ cudaError_t launch_stream_cfg(const PrepareArgs& a, unsigned* ctl) {
   stream_quantize_kernel<kD, TIn><<<kStreamCtas * sms, kStreamThreads, 0, a.stream>>>(
       reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), a.scales,
       reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp), reinterpret_cast<__half*>(a.Vt), ctl, ctl + 16,
-      ctl + 16 + 3 * (size_t)units, a.N, a.H, a.d, a.n_pad, units, a.rope);
+      ctl + 16 + 3 * (size_t)units, a.N, a.H, a.d, a.n_pad, units, a.rope, a.ld(), a.bs());
   return cudaGetLastError();
 }
 
@@ -883,7 +883,7 @@ cudaError_t launch_fused_cfg(const PrepareArgs& a) {
   dim3 grid(kClusterSize, a.B * a.H, 3);
   kern<<<grid, kFusedThreads, kFusedSmemBytes, a.stream>>>(
       reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), a.scales, reinterpret_cast<int8_t*>(a.Qp), reinterpret_cast<int8_t*>(a.Kp),
-      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
+      reinterpret_cast<__half*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope, a.ld(), a.bs());
   return cudaGetLastError();
 }
 
@@ -892,7 +892,7 @@ cudaError_t launch_prepare_cfg(const PrepareArgs& a) {
   dim3 grid(a.n_pad / kPrepRows, a.B * a.H, 3);
   prepare_kernel<kOut, kD, TIn><<<grid, kPrepThreads, 0, a.stream>>>(
       reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V),
-      a.scales, a.Qp, a.Kp, reinterpret_cast<uint16_t*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope);
+      a.scales, a.Qp, a.Kp, reinterpret_cast<uint16_t*>(a.Vt), a.N, a.H, a.d, a.n_pad, a.rope, a.ld(), a.bs());
   return cudaGetLastError();
 }
 
@@ -913,7 +913,7 @@ cudaError_t launch_absmax_t(const PrepareArgs& a, unsigned* amax_bits) {
   dim3 grid((a.N + kAbsmaxRows - 1) / kAbsmaxRows, a.B, 3);
   absmax_kernel<TIn><<<grid, kAbsmaxThreads, sizeof(unsigned) * a.H, a.stream>>>(
       reinterpret_cast<const TIn*>(a.Q), reinterpret_cast<const TIn*>(a.K), reinterpret_cast<const TIn*>(a.V), amax_bits,
-      a.N, a.H, a.d, a.d_pad, a.rope);
+      a.N, a.H, a.d, a.d_pad, a.rope, a.ld(), a.bs());
   return cudaGetLastError();
 }
 cudaError_t launch_absmax_d(const PrepareArgs& a, unsigned* amax_bits) { QMHA_BY_DTYPE(a, (launch_absmax_t<TIn>(a, amax_bits))) }

@@ -22,6 +22,11 @@ struct PrepareArgs {
   // fused RoPE (utils/verify.cu:9-23 applied to Q and K rows before absmax / quantisation):
   // table of {cos, sin}(pos * base^(-2k/d)) as float2 [N][d/2], built on the host; nullptr = off
   const float2* rope = nullptr;
+  // Q, K, V may be (batch, head-range) slabs of larger tensors: distance between consecutive rows / batch entries in
+  // elements (0 = dense: H*d and N*H*d); the same pitches for all three
+  long long in_ld = 0, in_bs = 0;
+  int ld() const { return in_ld > 0 ? (int)in_ld : H * d; }
+  size_t bs() const { return in_bs > 0 ? (size_t)in_bs : (size_t)N * (size_t)ld(); }
 };
 
 // absmax pass + scale finalisation (3 launches incl. the memset node).

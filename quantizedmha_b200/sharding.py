@@ -220,7 +220,7 @@ def forward_fused_gather(Q, K, V, H: int, rep: "ReplicatedOutput", kernel="int8"
     if fence:
         rep.fence()                      # nobody still reads the previous contents of any replica
     for b0, b1, h0, h1 in launch_plan(B, H, rep.world, rep.rank):
-        q, k, v = (t[b0:b1, :, h0 * d:h1 * d].contiguous() for t in (Q, K, V))
+        q, k, v = (t[b0:b1, :, h0 * d:h1 * d] for t in (Q, K, V))   # strided slab views: read in place by the quantise pass
         view = out[b0:b1, :, h0 * d:h1 * d]
         off = slab_offset(b0, h0, N, H, d) * esz
         peers = [rep.peer_base[r] + off for r in sorted(rep.peer_base)]

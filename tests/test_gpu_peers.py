@@ -202,3 +202,55 @@ def test_persistent_kernel_is_bit_identical(torch, qm, gran, monkeypatch):
         _sync(torch, qm)
         monkeypatch.setenv("QMHA_PERSIST", "1")
         assert torch.equal(small, small_ref)
+
+
+@pytest.mark.parametrize("kernel,gran,dtype", [("int8", "block", "float32"), ("int8", "head", "float32"),
+                                                ("int8", "tensor", "float32"), ("f16", "head", "float32"),
+                                                ("bf16", "head", "bfloat16"), ("int8", "block", "float16"),
+                                                ("int8_pv8", "block", "float32")])
+def test_strided_input_slabs_are_read_in_place(torch, qm, kernel, gran, dtype):
+    """Q, K, V as (batch, head-range) views of larger tensors (qmha_args.in_row_stride / in_batch_stride): every
+    quantise / convert kernel reads them in place; results equal the call on contiguous copies bit for bit."""
+    B_all, N, H_all, d, h0, h1 = 3, 333, 5, 64, 1, 4
+    heads = h1 - h0
+    dt = getattr(torch, dtype)
+    g = {"block": qm.GRAN_BLOCK, "head": qm.GRAN_HEAD, "tensor": qm.GRAN_TENSOR}[gran]
+    full = _inputs(torch, B_all, N + 2, H_all * d, seed=31, dtype=dt)
+    views = [t[1:3, :N, h0 * d:h1 * d] for t in full]
+    assert not views[0].is_contiguous()
+    ref = qm.forward(*(v.contiguous() for v in views), heads, kernel=kernel, gran=g)
+    _sync(torch, qm)
+    out = qm.forward(*views, heads, kernel=kernel, gran=g)
+    _sync(torch, qm)
+    assert torch.equal(out, ref)
+    # one batch entry, rope on (the rotation uses the row index inside the slab), 2-D views
+    ref2 = qm.forward(*(v[0].contiguous() for v in views), heads, kernel=kernel, gran=g, rope=True)
+    out2 = qm.forward(*(v[0] for v in views), heads, kernel=kernel, gran=g, rope=True)
+    _sync(torch, qm)
+    assert torch.equal(out2, ref2)
+
+
+def test_strided_inputs_with_the_persistent_per_head_quantiser_and_bad_pitches(torch, qm, monkeypatch):
+    import ctypes as C
+    B, N, heads, d = 2, 512, 2, 128
+    full = _inputs(torch, B, N, 3 * heads * d, seed=33)
+    views = [t[:, :, heads * d:2 * heads * d] for t in full]
+    ref = qm.forward(*(v.contiguous() for v in views), heads, kernel="int8", gran=qm.GRAN_HEAD)
+    monkeypatch.setenv("QMHA_STREAM_QUANT", "1")
+    out = qm.forward(*views, heads, kernel="int8", gran=qm.GRAN_HEAD)
+    _sync(torch, qm)
+    assert torch.equal(out, ref)
+    monkeypatch.delenv("QMHA_STREAM_QUANT")
+    a = qm.QmhaArgs()
+    qm.lib().qmha_args_init(C.byref(a))
+    o = torch.empty((B, N, heads * d), device="cuda")
+    a.Q, a.K, a.V, a.O = (views[0].data_ptr(), views[1].data_ptr(), views[2].data_ptr(), o.data_ptr())
+    a.B, a.N, a.d_model, a.h = B, N, heads * d, heads
+    a.in_row_stride = heads * d - 4                      # smaller than a row
+    assert qm.lib().qmha_forward_ex(C.byref(a)) != 0 and b"input strides" in qm.lib().qmha_last_error()
+    a.in_row_stride = 3 * heads * d + 1                  # not a multiple of 16 bytes
+    assert qm.lib().qmha_forward_ex(C.byref(a)) != 0 and b"16 bytes" in qm.lib().qmha_last_error()
+    a.in_row_stride, a.in_batch_stride = 3 * heads * d, N * 3 * heads * d
+    assert qm.lib().qmha_forward_ex(C.byref(a)) == 0
+    _sync(torch, qm)
+    assert torch.equal(o, qm.forward(*(v.contiguous() for v in views), heads, kernel="int8", gran=-1))
