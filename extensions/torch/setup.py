@@ -22,6 +22,7 @@ setup(
         name="torch_ext",
         sources=[os.path.join(here, "torch_ext.cpp")],
         include_dirs=[os.path.join(root, "include")],
+        depends=[os.path.join(root, "include", "qmha.h")],   # qmha_args carries its size: a stale build fails at run time
         library_dirs=[libdir],
         libraries=["qmha"],
         runtime_library_dirs=[libdir],
