@@ -181,10 +181,30 @@ class ReplicatedOutput:
             raise qb.QmhaError(f"at most {qb.MAX_PEERS + 1} ranks")
         self.B, self.N, self.H, self.d = B, N, H, d
         self.local = torch.empty((B, N, H * d), dtype=dtype or torch.float32, device=device)
-        mine = qb.ipc_export(self.local)
+        # Every step that can fail on one rank only is followed by an exchange of the outcome, so that all ranks raise
+        # together instead of leaving the others inside a collective.
+        try:
+            mine = qb.ipc_export(self.local)
+        except qb.QmhaError as e:
+            mine = ("error", str(e))
         handles = [None] * self.world
         dist.all_gather_object(handles, mine, group=group)
-        self.peer_base = {r: qb.ipc_open(h, off) for r, (h, off) in enumerate(handles) if r != self.rank}
+        bad = [f"rank {r}: {h[1]}" for r, h in enumerate(handles) if h[0] == "error"]
+        if bad:
+            raise qb.QmhaError("ReplicatedOutput: export failed (" + "; ".join(bad) + ")")
+        self.peer_base, err = {}, None
+        try:
+            for r, (h, off) in enumerate(handles):
+                if r != self.rank:
+                    self.peer_base[r] = qb.ipc_open(h, off)
+        except qb.QmhaError as e:
+            err = str(e)
+        outcomes = [None] * self.world
+        dist.all_gather_object(outcomes, err, group=group)
+        bad = [f"rank {r}: {o}" for r, o in enumerate(outcomes) if o]
+        if bad:
+            self.close()
+            raise qb.QmhaError("ReplicatedOutput: mapping a peer's replica failed (" + "; ".join(bad) + ")")
         self._fence = torch.zeros(1, dtype=torch.int32, device=self.local.device)
 
     def fence(self):
