@@ -105,6 +105,8 @@ typedef struct qmha_args {
    * heads hands over its columns of the full [B, N, H*d] tensors without a copy ("inputs / outputs for a
    * unit are the strided slices [b, :, h, :]"). */
   int64_t in_row_stride, in_batch_stride;
+  int device;               /* device ordinal that owns the pointers and the stream; -1 = the calling thread's current
+                               device (one workspace per device; the caller's current device is restored on return)  */
 } qmha_args;
 #define QMHA_MAX_PEERS 7
 void qmha_args_init(qmha_args* a);

@@ -32,7 +32,8 @@ class QmhaArgs(C.Structure):
                 ("gran", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int), ("rope", C.c_int),
                 ("rope_base", C.c_float), ("variant", C.c_int), ("stream", C.c_void_p),
                 ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64), ("n_peers", C.c_int),
-                ("peer_O", C.c_void_p * 7), ("in_row_stride", C.c_int64), ("in_batch_stride", C.c_int64)]
+                ("peer_O", C.c_void_p * 7), ("in_row_stride", C.c_int64), ("in_batch_stride", C.c_int64),
+                ("device", C.c_int)]
 
 
 MAX_PEERS = 7
@@ -138,9 +139,9 @@ def _torch():
     return torch
 
 
-def _stream_ptr(stream=None) -> int:
+def _stream_ptr(stream=None, device=None) -> int:
     torch = _torch()
-    s = stream if stream is not None else torch.cuda.current_stream()
+    s = stream if stream is not None else torch.cuda.current_stream(device)
     return int(s.cuda_stream)
 
 
@@ -236,7 +237,8 @@ def forward(Q, K, V, num_heads: int, kernel="int8", gran: int = GRAN_HEAD, out=N
     a.in_dtype, a.out_dtype = _dtype_id(Q.dtype), _dtype_id(out.dtype)
     a.rope = -1 if rope is None else int(bool(rope))
     a.rope_base = float(rope_base)
-    a.stream = _stream_ptr(stream)
+    a.stream = _stream_ptr(stream, Q.device)           # the tensors' device, which need not be the current one
+    a.device = Q.device.index if Q.device.index is not None else -1
     if (ld, bs) != (d_model, N * d_model):
         a.o_row_stride, a.o_batch_stride = ld, bs
     peers = list(peer_outs or [])

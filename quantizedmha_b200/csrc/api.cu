@@ -504,6 +504,7 @@ qmha_args make_args(const void* Q, const void* K, const void* V, void* O, int B,
   a.in_dtype = a.out_dtype = QMHA_DTYPE_F32;
   a.rope = -1; a.rope_base = 0.f; a.variant = -1;
   a.stream = stream;
+  a.device = -1;
   return a;
 }
 
@@ -682,7 +683,19 @@ int qmha_forward_ex(const qmha_args* args) {
     return fail("qmha_forward_ex: struct_size does not match this library's qmha_args (header / library mismatch)");
   qmha_args a = *args;
   if (resolve_args(&a)) return 1;
-  return forward_device(a);
+  if (a.device < 0) return forward_device(a);
+  // explicit device ordinal: run the call with that device current and put the caller's device back
+  int cur = 0, count = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess || cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return fail("no CUDA device (this library has no CPU fallback)");
+  }
+  if (a.device >= count) return fail("qmha_args.device: no such device");
+  if (a.device == cur) return forward_device(a);
+  if (cudaSetDevice(a.device) != cudaSuccess) { cudaGetLastError(); return fail("cudaSetDevice(qmha_args.device) failed"); }
+  const int rc = forward_device(a);
+  cudaSetDevice(cur);
+  return rc;
 }
 
 void qmha_args_init(qmha_args* a) {

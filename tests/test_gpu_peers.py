@@ -147,6 +147,33 @@ def test_ipc_export_of_a_torch_tensor(torch, qm):
     del a
 
 
+def test_device_ordinal_in_the_argument_block(torch, qm):
+    """qmha_args.device: the call runs on the device that owns the tensors whatever the caller's current device is,
+    and leaves the current device alone; a wrong ordinal fails loudly."""
+    import ctypes as C
+    q, k, v = _inputs(torch, 1, 300, 128, seed=41)
+    ref = qm.forward(q, k, v, 2)
+    _sync(torch, qm)
+    a = qm.QmhaArgs()
+    qm.lib().qmha_args_init(C.byref(a))
+    assert a.device == -1
+    o = torch.empty_like(q)
+    a.Q, a.K, a.V, a.O = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    a.B, a.N, a.d_model, a.h, a.gran = 1, 300, 128, 2, qm.GRAN_HEAD
+    a.device = torch.cuda.device_count()
+    assert qm.lib().qmha_forward_ex(C.byref(a)) != 0 and b"no such device" in qm.lib().qmha_last_error()
+    a.device = 0
+    assert qm.lib().qmha_forward_ex(C.byref(a)) == 0
+    _sync(torch, qm)
+    assert torch.equal(o, ref)
+    if torch.cuda.device_count() >= 2:                    # tensors on GPU 1 while GPU 0 is current
+        q1, k1, v1 = (t.to("cuda:1") for t in (q, k, v))
+        assert torch.cuda.current_device() == 0
+        o1 = qm.forward(q1, k1, v1, 2)
+        torch.cuda.synchronize(1)
+        assert torch.cuda.current_device() == 0 and torch.equal(o1.cpu(), ref.cpu())
+
+
 def test_replica_on_a_second_gpu_in_one_process(torch, qm):
     """The NVLink leg without process boundaries: the kernel runs on GPU 0 and its epilogue also stores into a replica
     that lives on GPU 1 (peer access enabled through the library)."""
