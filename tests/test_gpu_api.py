@@ -301,6 +301,16 @@ def test_two_devices_in_one_process(qm, torch, oracle):
     assert torch.equal(outs[0].cpu(), outs[1].cpu())
 
 
+def test_plain_c_consumer_of_the_abi(torch, tmp_path):
+    """tests/c/abi_consumer.c: solve() and qmha_forward_ex() (FP16 kernel, strided output slab) called from C with
+    memory from the CUDA runtime's C API — no Python, no torch on the path under test."""
+    import quantizedmha_b200 as qm
+    from test_host_cpu import _build_c_consumer
+    exe = _build_c_consumer(qm, tmp_path)
+    r = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "abi_consumer ok" in r.stdout, r.stdout + r.stderr
+
+
 # ---------------------------------------------------------------------------------- the CLI half of the boundary
 def _profile_binary(kernel):
     path = os.path.join(ROOT, "bin", f"profile_{kernel}")

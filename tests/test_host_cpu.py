@@ -33,6 +33,28 @@ def test_library_exports_every_declared_symbol(qm):
         assert hasattr(L, n), f"{n} declared in include/qmha.h but not exported"
 
 
+def _build_c_consumer(qm, tmp):
+    """gcc (C99, warnings are errors) on tests/c/abi_consumer.c against include/qmha.h and libqmha.so."""
+    exe = os.path.join(str(tmp), "abi_consumer")
+    libdir = os.path.dirname(qm.lib_path())
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_consumer.c"), "-o", exe, "-L", libdir, "-lqmha",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", f"-Wl,-rpath,{libdir}",
+                    f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}"], check=True)
+    return exe
+
+
+def test_header_is_valid_c_and_the_argument_block_matches_the_library(qm, tmp_path):
+    """The boundary is a C ABI: a C99 translation unit includes qmha.h, links every entry it uses and sees the same
+    qmha_args size as the library and as the ctypes mirror."""
+    exe = _build_c_consumer(qm, tmp_path)
+    r = subprocess.run([exe, "sizes"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    c_size, stamped, kid = (int(x) for x in r.stdout.split())
+    assert c_size == stamped == ctypes.sizeof(qm.QmhaArgs) and kid == qm.KERNEL_INT8
+
+
 def test_launchers_header_is_the_reference_signature():
     txt = open(os.path.join(ROOT, "include", "qmha.h")).read()
     flat = " ".join(txt.split())
