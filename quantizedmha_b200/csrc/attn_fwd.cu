@@ -550,6 +550,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   bool dead = false;
 
   if (err_flag.raised()) return;  // an earlier CTA of this launch already failed: drain the grid
+  // Replicated output (peer_O): the CTAs of a wave finish together, so their NVLink stores would all drain at the same
+  // time while nothing computes, and then everything computes while the links idle.  Every other CTA of the FIRST wave
+  // starts late by about the drain time of half a wave: from then on one half of the SMs computes while the other half's
+  // stores drain (see launch_cfg for the estimate).
+  if (prm.stagger_ns != 0u) {
+    const unsigned lin = kPersist ? blockIdx.x : blockIdx.y * gridDim.x + blockIdx.x;
+    if (lin < prm.stagger_ctas && (lin & 1u)) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do {
+        __nanosleep(2000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      } while (t1 - t0 < (unsigned long long)prm.stagger_ns);
+    }
+  }
   const long long t_entry = (prm.cycles != nullptr && threadIdx.x == 0) ? clock64() : 0;
   // traced build: a CTA from the middle of the run (steady state, warm caches); phase stamps of its
   // warp 0 go behind the per-step stamps: entry, setup done, first scores, last P, O final, stores, exit
@@ -1539,6 +1554,23 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
   p.o_bs = (long long)o_bs;
   p.n_peers = a.n_peers;
   for (int pe = 0; pe < kMaxPeers; ++pe) p.peer_O[pe] = pe < a.n_peers ? a.peer_O[pe] : nullptr;
+  p.stagger_ns = 0u;
+  p.stagger_ctas = 0u;
+  if (a.n_peers > 0) {
+    // drain time of half a wave of CTAs at ~750 GB/s of NVLink egress (one CTA sends 256 rows x d x n_peers elements);
+    // never more than half of a CTA's own running time (~1400 clk per 64-key half-step at ~1.9 GHz)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const double bytes_cta = 2.0 * kBM * a.d * (double)o_elt * a.n_peers;
+    double ns = bytes_cta * (sms / 2) / 750.0;
+    const double cta_ns = (double)((a.N + kHN - 1) / kHN) * 1400.0 / 1.9;
+    if (ns > 0.9 * cta_ns) ns = 0.9 * cta_ns;
+    const char* e = getenv("QMHA_PEER_STAGGER_NS");      // tuning aid: 0 switches the stagger off
+    if (e && *e) ns = atof(e);
+    p.stagger_ns = (unsigned)ns;
+    p.stagger_ctas = (unsigned)sms;
+  }
   dim3 grid((a.N + 2 * kBM - 1) / (2 * kBM), (unsigned)units, 1);
   p.n_qblocks = (int)grid.x;
   p.n_items = (int)(grid.x * units);

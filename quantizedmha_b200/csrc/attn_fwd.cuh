@@ -34,6 +34,8 @@ struct AttnParams {
   long long o_ld, o_bs; // distance between consecutive rows / batch entries of O in elements (dense: H*d, N*H*d)
   int n_qblocks;        // 256-row query blocks per unit
   int n_items;          // work items (unit, query block) of the launch: n_qblocks * units (persistent kernel)
+  unsigned stagger_ns;  // replicated output: odd CTAs of the first wave start this much later (0 = off) ...
+  unsigned stagger_ctas;   // ... "first wave" = linear CTA index below this
   int n_peers;          // further destinations that receive the same bytes (replicas on NVLink peers)
   void* peer_O[kMaxPeers];
 };
