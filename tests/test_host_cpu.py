@@ -195,6 +195,28 @@ print("ok", rank)
 """
 
 
+def test_slab_stride_detection_of_the_ctypes_mirror(qm):
+    """binding._out_strides: (row pitch, batch pitch) in elements of a tensor that may be a (batch, head-range) view;
+    what forward() hands to qmha_args.o_row_stride / in_row_stride.  Pure host logic: CPU tensors suffice."""
+    import torch
+    f = qm.binding._out_strides
+    full = torch.zeros((4, 100, 640))
+    assert f(full, 4, 100, 640) == (640, 100 * 640)
+    assert f(full[1:3, :, 128:384], 2, 100, 256) == (640, 100 * 640)            # heads 1..2 of batch entries 1..2
+    assert f(full[2, :, 128:384], 1, 100, 256) == (640, 100 * 640)              # 2-D view of one batch entry
+    assert f(full[:, :60, :], 4, 60, 640) == (640, 100 * 640)                   # fewer rows than the parent
+    assert f(torch.zeros((100, 256)), 1, 100, 256) == (256, 100 * 256)
+    assert f(torch.zeros((1, 1, 64)), 1, 1, 64) == (64, 64)                     # N = 1: nothing to stride over
+    for bad, args in ((torch.zeros((256, 100)).t(), (1, 100, 256)),              # last dimension not contiguous
+                      (torch.zeros((2, 100, 256)), (1, 100, 256)),               # wrong shape
+                      (torch.zeros((100, 256)), (2, 100, 256))):                 # 2-D tensor for a batched call
+        with pytest.raises(qm.QmhaError):
+            f(bad, *args)
+    a = qm.QmhaArgs()
+    qm.lib().qmha_args_init(ctypes.byref(a))
+    assert (a.o_row_stride, a.o_batch_stride, a.in_row_stride, a.in_batch_stride, a.n_peers, a.device) == (0, 0, 0, 0, 0, -1)
+
+
 def test_fused_gather_launch_plan_covers_every_unit_once():
     from quantizedmha_b200.sharding import launch_plan, slab_offset, unit_range
     for B, H, W in [(8, 32, 8), (32, 32, 8), (8, 32, 3), (1, 8, 2), (5, 7, 4), (2, 3, 8)]:
