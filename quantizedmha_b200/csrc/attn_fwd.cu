@@ -1566,6 +1566,9 @@ bool launch_cfg(const AttnLaunch& a, std::string* err) {
     double ns = bytes_cta * (sms / 2) / 750.0;
     const double cta_ns = (double)((a.N + kHN - 1) / kHN) * 1400.0 / 1.9;
     if (ns > 0.9 * cta_ns) ns = 0.9 * cta_ns;
+    // only worth its delay when the launch runs for several waves (a short launch would just finish later)
+    const long long ctas = (long long)((a.N + 2 * kBM - 1) / (2 * kBM)) * (long long)units;
+    if (ctas < 3LL * sms) ns = 0.0;
     const char* e = getenv("QMHA_PEER_STAGGER_NS");      // tuning aid: 0 switches the stagger off
     if (e && *e) ns = atof(e);
     p.stagger_ns = (unsigned)ns;
